@@ -1,0 +1,87 @@
+"""ctypes binding of libhbegp.so (include/hbegp.h).  There is no CPU fallback: a missing or
+unloadable library is an ImportError, and every compute call fails on a box without a GPU."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhbegp.so")
+
+F64, F32 = 0, 1
+OK, NOT_PD = 0, 1
+ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_NO_CAPTURE = -1, -2, -3, -4, -5
+
+
+class RunResult(C.Structure):
+    _fields_ = [
+        ("best_lml", C.c_double),
+        ("best_eval", C.c_longlong),
+        ("n_evals", C.c_longlong),
+        ("final_f", C.c_double),
+        ("status", C.c_int),
+        ("reserved", C.c_int),
+    ]
+
+
+OBJECTIVE_FN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+
+# name -> (restype, argtypes); must list every symbol include/hbegp.h declares
+PROTOTYPES = {
+    "hbegp_version": (C.c_char_p, []),
+    "hbegp_last_error": (C.c_char_p, []),
+    "hbegp_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "hbegp_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "hbegp_ctx_set_workspace_limit": (C.c_int, [C.c_void_p, C.c_ulonglong]),
+    "hbegp_ctx_launch_count": (C.c_longlong, [C.c_void_p]),
+    "hbegp_set_data": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p]),
+    "hbegp_set_data_device": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p]),
+    "hbegp_lml_grad_batch": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hbegp_fit_runs": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                 C.POINTER(RunResult), C.c_void_p]),
+    "hbegp_pick_best_run": (C.c_int, [C.c_int, C.POINTER(RunResult)]),
+    "hbegp_model_create": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_void_p, C.c_void_p]),
+    "hbegp_model_destroy": (C.c_int, [C.c_void_p]),
+    "hbegp_model_n": (C.c_long, [C.c_void_p]),
+    "hbegp_model_dim": (C.c_int, [C.c_void_p]),
+    "hbegp_predict": (C.c_int, [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_long)]),
+    "hbegp_predict_device": (C.c_int, [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hbegp_minimize_by_gradient": (C.c_int, [OBJECTIVE_FN, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_int, C.POINTER(C.c_double)]),
+    "hbegp_rng_seed": (None, [C.c_ulonglong, C.POINTER(C.c_ulonglong)]),
+    "hbegp_rng_fork": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
+    "hbegp_rng_uniform": (C.c_double, [C.POINTER(C.c_ulonglong), C.c_double, C.c_double]),
+    "hbegp_debug_factor": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.POINTER(C.c_int)]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C hbetune_rs_b200/csrc`).  hbetune_rs_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+class HbegpError(RuntimeError):
+    def __init__(self, code: int, where: str):
+        msg = lib.hbegp_last_error().decode("utf-8", "replace")
+        super().__init__(f"{where} failed with status {code}: {msg}")
+        self.code = code
+
+
+def check(code: int, where: str) -> int:
+    if code < 0:
+        raise HbegpError(code, where)
+    return code

@@ -1,0 +1,310 @@
+// Tiled, batched, triangular-aware GEMM for the GP hot path (sm_100a).
+//
+// FP64 runs on the DMMA tensor pipe (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; there is no tcgen05 f64
+// kind), FP32 (--use-32) on plain FFMA (TF32 would break the 1e-4 parity bound).  Operand tiles are
+// staged global -> shared with 16-byte cp.async (LDGSTS) through a 3-stage ring; shared rows are padded
+// so that the 8x4 DMMA fragment reads are bank-conflict free.
+//
+// One kernel serves every dense contraction of the path (potrf panel solve + trailing SYRK, triangular
+// inverse merges, W^T W, and the predictive-variance product): C = alpha * A(.,k) B(.,k)^T + beta * C
+// where each operand is either k-contiguous ("KMAJOR": X[i*ld + k]) or i-contiguous (X[k*ld + i]), the
+// k range of a tile may be cut by the triangular structure of an operand (KMode), only the lower tiles of
+// C may be produced, and the epilogue either stores C or emits per-row sums of squares.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <type_traits>
+
+namespace hbegp {
+
+enum KMode : int {
+    K_FULL = 0,
+    K_LE_N = 1,  // k in [0, n0 + BN)      (B lower-triangular, indexed [n][k])
+    K_GE_N = 2,  // k in [n0, K)           (B lower-triangular, indexed [k][n])
+    K_LE_M = 3,  // k in [0, m0 + BM)      (A lower-triangular, indexed [m][k])
+    K_GE_M = 4,  // k in [m0, K)           (A lower-triangular, indexed [k][m])
+};
+
+template <typename T>
+struct GemmArgs {
+    const T* A;
+    const T* B;
+    T* C;
+    long lda, ldb, ldc;
+    long sA, sB, sC;  // batch strides in elements
+    int M, N, K;
+    int kmode;
+    int lower_only;  // produce only tiles with m0 >= n0 (BM == BN)
+    T alpha, beta;
+    T* rowsumsq;  // if non-null: partial[(row) * ld_rs + tile_n] = sum_j acc(row, j)^2, C untouched
+    long ld_rs, s_rs;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <typename T, int BM, int BN, int WM, int WN, bool A_KMAJOR, bool B_KMAJOR>
+struct GemmCfg {
+    static constexpr int BK = 16;
+    static constexpr int PAD = 4;
+    static constexpr int STAGES = 3;
+    static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+    static constexpr int THREADS = WARPS_M * WARPS_N * 32;
+    static constexpr int VEC = 16 / sizeof(T);
+    static constexpr int A_STRIDE = A_KMAJOR ? (BK + PAD) : (BM + PAD);
+    static constexpr int B_STRIDE = B_KMAJOR ? (BK + PAD) : (BN + PAD);
+    static constexpr int A_ELEMS = A_KMAJOR ? BM * A_STRIDE : BK * A_STRIDE;
+    static constexpr int B_ELEMS = B_KMAJOR ? BN * B_STRIDE : BK * B_STRIDE;
+    static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_ELEMS * sizeof(T);
+};
+
+// Copies one operand tile (R rows of the tile dimension x BK of k) into shared memory.
+template <typename T, int R, int BK, int STRIDE, bool KMAJOR, int THREADS>
+__device__ __forceinline__ void load_tile(T* __restrict__ s, const T* __restrict__ g, long ld, int r0, int k0,
+                                          int tid) {
+    constexpr int VEC = 16 / sizeof(T);
+    if (KMAJOR) {
+        constexpr int CPR = BK / VEC;  // chunks per row
+        constexpr int TOTAL = R * CPR;
+#pragma unroll
+        for (int c = tid; c < TOTAL; c += THREADS) {
+            int row = c / CPR, cc = c % CPR;
+            cp_async16(s + row * STRIDE + cc * VEC, g + (long)(r0 + row) * ld + k0 + cc * VEC);
+        }
+    } else {
+        constexpr int CPR = R / VEC;
+        constexpr int TOTAL = BK * CPR;
+#pragma unroll
+        for (int c = tid; c < TOTAL; c += THREADS) {
+            int kk = c / CPR, cc = c % CPR;
+            cp_async16(s + kk * STRIDE + cc * VEC, g + (long)(k0 + kk) * ld + r0 + cc * VEC);
+        }
+    }
+}
+
+template <typename T, int BM, int BN, int WM, int WN, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR>::THREADS)
+    gemm_kernel(const GemmArgs<T> p) {
+    using Cfg = GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR>;
+    constexpr int BK = Cfg::BK, STAGES = Cfg::STAGES, THREADS = Cfg::THREADS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* smem = reinterpret_cast<T*>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / Cfg::WARPS_N, wn = warp % Cfg::WARPS_N;
+    const int tiles_m = p.M / BM, tiles_n = p.N / BN;
+
+    // ---- tile coordinates (heavy tiles first for the triangular k ranges)
+    int mt, nt;
+    {
+        int t = blockIdx.x;
+        if (p.lower_only) {
+            // enumerate mt >= nt, row by row
+            int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while ((long)(r + 1) * (r + 2) / 2 <= t) ++r;
+            while ((long)r * (r + 1) / 2 > t) --r;
+            mt = r;
+            nt = t - r * (r + 1) / 2;
+            if (p.kmode != K_GE_M) {  // SYRK-like: uniform work, keep order
+            }
+        } else if (p.kmode == K_LE_M) {
+            mt = tiles_m - 1 - t / tiles_n;
+            nt = t % tiles_n;
+        } else if (p.kmode == K_LE_N) {
+            nt = tiles_n - 1 - t / tiles_m;
+            mt = t % tiles_m;
+        } else {
+            nt = t / tiles_m;
+            mt = t % tiles_m;
+        }
+    }
+    const int m0 = mt * BM, n0 = nt * BN;
+    int kbeg = 0, kend = p.K;
+    if (p.kmode == K_LE_N) kend = min(p.K, n0 + BN);
+    else if (p.kmode == K_GE_N) kbeg = n0;
+    else if (p.kmode == K_LE_M) kend = min(p.K, m0 + BM);
+    else if (p.kmode == K_GE_M) kbeg = m0;
+    const int nk = (kend - kbeg) / BK;
+
+    const T* gA = p.A + (long)blockIdx.z * p.sA;
+    const T* gB = p.B + (long)blockIdx.z * p.sB;
+
+    auto issue = [&](int kt) {
+        T* sA = smem + (kt % STAGES) * Cfg::STAGE_ELEMS;
+        T* sB = sA + Cfg::A_ELEMS;
+        int k0 = kbeg + kt * BK;
+        load_tile<T, BM, BK, Cfg::A_STRIDE, A_KMAJOR, THREADS>(sA, gA, p.lda, m0, k0, tid);
+        load_tile<T, BN, BK, Cfg::B_STRIDE, B_KMAJOR, THREADS>(sB, gB, p.ldb, n0, k0, tid);
+    };
+
+    constexpr bool F64 = std::is_same<T, double>::value;
+    constexpr int FM = WM / 8;               // f64: 8-row mma tiles; f32: rows per thread
+    constexpr int FN = F64 ? WN / 8 : WN / 4;  // f64: 8-col mma tiles; f32: cols per thread
+    constexpr int ACC = F64 ? 2 : 1;
+    T acc[FM][FN][ACC];
+#pragma unroll
+    for (int i = 0; i < FM; i++)
+#pragma unroll
+        for (int j = 0; j < FN; j++)
+#pragma unroll
+            for (int e = 0; e < ACC; e++) acc[i][j][e] = T(0);
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nk) issue(s);
+        cp_async_commit();
+    }
+
+    const int lr = lane >> 2, lc = lane & 3;
+    for (int kt = 0; kt < nk; kt++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (kt + STAGES - 1 < nk) issue(kt + STAGES - 1);
+        cp_async_commit();
+        const T* sA = smem + (kt % STAGES) * Cfg::STAGE_ELEMS;
+        const T* sB = sA + Cfg::A_ELEMS;
+        if constexpr (F64) {
+#pragma unroll
+            for (int ks = 0; ks < BK / 4; ks++) {
+                T a[FM], b[FN];
+                const int k = ks * 4 + lc;
+#pragma unroll
+                for (int i = 0; i < FM; i++) {
+                    int row = wm * WM + i * 8 + lr;
+                    a[i] = A_KMAJOR ? sA[row * Cfg::A_STRIDE + k] : sA[k * Cfg::A_STRIDE + row];
+                }
+#pragma unroll
+                for (int j = 0; j < FN; j++) {
+                    int col = wn * WN + j * 8 + lr;
+                    b[j] = B_KMAJOR ? sB[col * Cfg::B_STRIDE + k] : sB[k * Cfg::B_STRIDE + col];
+                }
+#pragma unroll
+                for (int i = 0; i < FM; i++)
+#pragma unroll
+                    for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < BK; k++) {
+                T a[FM], b[FN];
+#pragma unroll
+                for (int i = 0; i < FM; i++) {
+                    int row = wm * WM + i * 8 + lr;
+                    a[i] = A_KMAJOR ? sA[row * Cfg::A_STRIDE + k] : sA[k * Cfg::A_STRIDE + row];
+                }
+#pragma unroll
+                for (int j = 0; j < FN; j++) {
+                    int col = wn * WN + j * 4 + lc;
+                    b[j] = B_KMAJOR ? sB[col * Cfg::B_STRIDE + k] : sB[k * Cfg::B_STRIDE + col];
+                }
+#pragma unroll
+                for (int i = 0; i < FM; i++)
+#pragma unroll
+                    for (int j = 0; j < FN; j++) acc[i][j][0] = fmaf(a[i], b[j], acc[i][j][0]);
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue
+    if (p.rowsumsq != nullptr) {
+        __syncthreads();  // operand ring is dead: reuse it as the cross-warp reduction buffer
+        T* red = smem;    // [BM][WARPS_N]
+#pragma unroll
+        for (int i = 0; i < FM; i++) {
+            T s = T(0);
+#pragma unroll
+            for (int j = 0; j < FN; j++)
+#pragma unroll
+                for (int e = 0; e < ACC; e++) s += acc[i][j][e] * acc[i][j][e];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (lc == 0) red[(wm * WM + i * 8 + lr) * Cfg::WARPS_N + wn] = s;
+        }
+        __syncthreads();
+        T* out = p.rowsumsq + (long)blockIdx.z * p.s_rs;
+        for (int r = tid; r < BM; r += THREADS) {
+            T s = T(0);
+#pragma unroll
+            for (int w = 0; w < Cfg::WARPS_N; w++) s += red[r * Cfg::WARPS_N + w];
+            out[(long)(m0 + r) * p.ld_rs + nt] = s;
+        }
+        return;
+    }
+
+    T* gC = p.C + (long)blockIdx.z * p.sC;
+    const bool use_beta = (p.beta != T(0));
+#pragma unroll
+    for (int i = 0; i < FM; i++) {
+        const long row = m0 + wm * WM + i * 8 + lr;
+#pragma unroll
+        for (int j = 0; j < FN; j++) {
+            if constexpr (F64) {
+                const int col = n0 + wn * WN + j * 8 + 2 * lc;
+                double2* ptr = reinterpret_cast<double2*>(gC + row * p.ldc + col);
+                double2 v;
+                v.x = p.alpha * acc[i][j][0];
+                v.y = p.alpha * acc[i][j][1];
+                if (use_beta) {
+                    double2 o = *ptr;
+                    v.x += p.beta * o.x;
+                    v.y += p.beta * o.y;
+                }
+                *ptr = v;
+            } else {
+                const int col = n0 + wn * WN + j * 4 + lc;
+                T* ptr = gC + row * p.ldc + col;
+                T v = p.alpha * acc[i][j][0];
+                if (use_beta) v += p.beta * (*ptr);
+                *ptr = v;
+            }
+        }
+    }
+}
+
+template <typename T, int BM, int BN, int WM, int WN, bool AK, bool BK_>
+inline cudaError_t launch_gemm_cfg(const GemmArgs<T>& a, int batch, cudaStream_t stream) {
+    using Cfg = GemmCfg<T, BM, BN, WM, WN, AK, BK_>;
+    auto kern = gemm_kernel<T, BM, BN, WM, WN, AK, BK_>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    long tm = a.M / BM, tn = a.N / BN;
+    long tiles = a.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+    if (tiles <= 0 || batch <= 0) return cudaSuccess;
+    dim3 grid((unsigned)tiles, 1, (unsigned)batch);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// Picks the CTA tile: 128x128 (8 warps, 64x32 warp tiles) when the problem tiles evenly and is large
+// enough to fill the machine, else 64x64 (4 warps, 32x32 warp tiles).
+template <typename T, bool AK, bool BK_>
+inline cudaError_t launch_gemm(const GemmArgs<T>& a, int batch, cudaStream_t stream, int force_tile = 0) {
+    bool can128 = (a.M % 128 == 0) && (a.N % 128 == 0);
+    long tiles128 = can128 ? (a.lower_only ? (long)(a.M / 128) * (a.M / 128 + 1) / 2 : (long)(a.M / 128) * (a.N / 128)) : 0;
+    bool use128 = can128 && tiles128 * batch >= 148;
+    if (force_tile == 64) use128 = false;
+    if (force_tile == 128 && can128) use128 = true;
+    if (use128) return launch_gemm_cfg<T, 128, 128, 64, 32, AK, BK_>(a, batch, stream);
+    return launch_gemm_cfg<T, 64, 64, 32, 32, AK, BK_>(a, batch, stream);
+}
+
+}  // namespace hbegp

@@ -1,0 +1,833 @@
+// libhbegp.so — C ABI (include/hbegp.h) over the sm_100a kernels in gemm.cuh / kernels.cuh.
+//
+// One evaluation of the reference's lml_with_gradient (src/gpr/lml.rs:29-79) is, on the device:
+//   scale X -> assemble K (lower tiles) -> recursive Cholesky fused with the triangular inverse
+//   (L and W = L^-1 come out together; panel solves, trailing SYRKs and inverse merges are DMMA GEMMs)
+//   -> alpha = W^T (W y) -> K^-1 = W^T W (lower tiles, DMMA) -> fused gradient contraction -> finish.
+// Evaluations are batched: every kernel carries the batch index in grid.z, and the batch is split over
+// a few CUDA streams so that the latency-bound 64x64 leaves of one group overlap the GEMMs of another.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/hbegp.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+#include "lbfgs.h"
+
+namespace hbegp {
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            int _code = (_e == cudaErrorMemoryAllocation) ? HBEGP_ERR_NOMEM : HBEGP_ERR_CUDA;            \
+            return fail(_code, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ +    \
+                                   ":" + std::to_string(__LINE__) + ")");                                \
+        }                                                                                                \
+    } while (0)
+
+static inline int round_up(long v, int m) { return (int)(((v + m - 1) / m) * m); }
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return HBEGP_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        CUDA_TRY(cudaMalloc(&p, need));
+        bytes = need;
+        return HBEGP_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+struct Model;
+
+struct EngineBase {
+    int device = 0, dtype = HBEGP_F64;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::vector<cudaStream_t> sub;
+    std::vector<cudaEvent_t> sub_done;
+    cudaEvent_t fork_ev = nullptr;
+    long n = 0;
+    int d = 0, np = 0;
+    size_t ws_limit = 0;
+    long long launches = 0;
+    std::vector<Model*> models;  // live models of this context (orphaned, not leaked, on ctx_destroy)
+    virtual ~EngineBase() {}
+    virtual int set_data(long n, int d, const void* x, const void* y, bool on_device) = 0;
+    virtual int eval_batch(double nu, int B, const double* theta, const double* lo, const double* hi, double* lml,
+                           double* grad, int* status) = 0;
+    virtual int model_create(double nu, const double* theta, const double* lo, const double* hi, Model** out,
+                             double* lml, void* alpha_out, void* kinv_out) = 0;
+    virtual int debug_factor(double nu, const double* theta, void* k, void* w, void* kinv, int* status) = 0;
+};
+
+struct Model {
+    EngineBase* eng = nullptr;
+    int dtype = 0;
+    long n = 0;
+    int d = 0, np = 0, nu2 = 5;
+    double c = 1.0;
+    DevBuf W, alpha, xsT, ls;  // inverse Cholesky factor (np x np), alpha (np), scaled X^T (d x np), length scales
+    DevBuf kstar, part, nbelow, xs_tmp, mean_tmp, var_tmp;
+    void release_all() {
+        W.release(); alpha.release(); xsT.release(); ls.release();
+        kstar.release(); part.release(); nbelow.release(); xs_tmp.release(); mean_tmp.release(); var_tmp.release();
+    }
+    virtual ~Model() {
+        release_all();
+        if (eng) eng->models.erase(std::remove(eng->models.begin(), eng->models.end(), this), eng->models.end());
+    }
+    virtual int predict_device(long m, const void* xs, void* mean, void* var, long* n_below_device) = 0;
+    virtual int predict_host(long m, const void* xs, void* mean, void* var, long* n_below) = 0;
+};
+
+static int nu_to_nu2(double nu, int* nu2) {
+    const double eps = std::numeric_limits<double>::epsilon();
+    if (std::fabs(nu - 0.5) <= eps) *nu2 = 1;
+    else if (std::fabs(nu - 1.5) <= eps) *nu2 = 3;
+    else if (std::fabs(nu - 2.5) <= eps) *nu2 = 5;
+    else return fail(HBEGP_ERR_UNSUPPORTED, "Matern kernel with arbitrary values for nu (matern_kernel.rs:79)");
+    return HBEGP_OK;
+}
+
+template <typename T>
+struct ModelT;
+
+template <typename T>
+struct Engine : EngineBase {
+    DevBuf dX, dY;
+    // batched workspaces (capacity `cap` evaluations)
+    int cap = 0;
+    DevBuf A, W, xsT, prm, u, alpha, ldp, tpart, gpart, d_lml, d_grad, d_status;
+    T* h_prm = nullptr;  // pinned staging
+    double* h_out = nullptr;
+    int* h_status = nullptr;
+    size_t h_prm_bytes = 0, h_out_bytes = 0, h_status_bytes = 0;
+
+    ~Engine() override {
+        for (DevBuf* b : {&dX, &dY, &A, &W, &xsT, &prm, &u, &alpha, &ldp, &tpart, &gpart, &d_lml, &d_grad, &d_status})
+            b->release();
+        if (h_prm) cudaFreeHost(h_prm);
+        if (h_out) cudaFreeHost(h_out);
+        if (h_status) cudaFreeHost(h_status);
+    }
+
+    int p() const { return d + 2; }
+    long mstride() const { return (long)np * np; }
+    int ntiles_lower() const { int t = np / TILE; return t * (t + 1) / 2; }
+    int nchunks() const { return (np + 255) / 256; }
+
+    int set_data(long n_, int d_, const void* x, const void* y, bool on_device) override {
+        if (n_ <= 0 || d_ <= 0 || !x || !y) return fail(HBEGP_ERR_INVALID, "set_data: n, d must be positive and x, y non-null");
+        if (n_ > 46000) return fail(HBEGP_ERR_INVALID, "set_data: n too large for a single-GPU factorisation");
+        CUDA_TRY(cudaSetDevice(device));
+        n = n_;
+        d = d_;
+        np = round_up(n, TILE);
+        int rc;
+        if ((rc = dX.ensure((size_t)n * d * sizeof(T)))) return rc;
+        if ((rc = dY.ensure((size_t)np * sizeof(T)))) return rc;
+        cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        CUDA_TRY(cudaMemsetAsync(dY.p, 0, (size_t)np * sizeof(T), stream));
+        CUDA_TRY(cudaMemcpyAsync(dX.p, x, (size_t)n * d * sizeof(T), kind, stream));
+        CUDA_TRY(cudaMemcpyAsync(dY.p, y, (size_t)n * sizeof(T), kind, stream));
+        if (!on_device) CUDA_TRY(cudaStreamSynchronize(stream));  // the caller may free x / y
+        cap = 0;  // workspaces are re-sized lazily
+        return HBEGP_OK;
+    }
+
+    size_t per_slot_bytes() const {
+        size_t s = 2 * (size_t)np * np * sizeof(T);
+        s += (size_t)d * np * sizeof(T) + (size_t)p() * sizeof(T) + 2 * (size_t)np * sizeof(T);
+        s += (size_t)(np / TILE) * sizeof(T) + (size_t)nchunks() * np * sizeof(T);
+        s += (size_t)ntiles_lower() * p() * sizeof(double) + (size_t)(p() + 1) * sizeof(double) + sizeof(int);
+        return s;
+    }
+
+    int ensure_capacity(int want) {
+        if (n <= 0) return fail(HBEGP_ERR_INVALID, "no training data: call hbegp_set_data first");
+        if (want <= cap) return HBEGP_OK;
+        size_t limit = ws_limit;
+        if (limit == 0) {
+            size_t fr = 0, tot = 0;
+            CUDA_TRY(cudaMemGetInfo(&fr, &tot));
+            // memory already held by the current workspaces is reusable
+            size_t held = A.bytes + W.bytes + gpart.bytes + tpart.bytes + xsT.bytes;
+            limit = (size_t)((double)(fr + held) * 0.7);
+        }
+        size_t per = per_slot_bytes();
+        int fit = (int)std::min<size_t>(limit / per, 4096);
+        if (fit < 1) return fail(HBEGP_ERR_NOMEM, "workspace limit too small for one n x n evaluation");
+        int newcap = std::min(want, fit);
+        if (newcap <= cap) return HBEGP_OK;
+        int rc;
+        size_t c = (size_t)newcap;
+        if ((rc = A.ensure(c * np * np * sizeof(T)))) return rc;
+        if ((rc = W.ensure(c * np * np * sizeof(T)))) return rc;
+        if ((rc = xsT.ensure(c * d * np * sizeof(T)))) return rc;
+        if ((rc = prm.ensure(c * p() * sizeof(T)))) return rc;
+        if ((rc = u.ensure(c * np * sizeof(T)))) return rc;
+        if ((rc = alpha.ensure(c * np * sizeof(T)))) return rc;
+        if ((rc = ldp.ensure(c * (np / TILE) * sizeof(T)))) return rc;
+        if ((rc = tpart.ensure(c * nchunks() * np * sizeof(T)))) return rc;
+        if ((rc = gpart.ensure(c * ntiles_lower() * p() * sizeof(double)))) return rc;
+        if ((rc = d_lml.ensure(c * sizeof(double)))) return rc;
+        if ((rc = d_grad.ensure(c * p() * sizeof(double)))) return rc;
+        if ((rc = d_status.ensure(c * sizeof(int)))) return rc;
+        if (h_prm_bytes < c * p() * sizeof(T)) {
+            if (h_prm) cudaFreeHost(h_prm);
+            h_prm_bytes = c * p() * sizeof(T);
+            CUDA_TRY(cudaMallocHost((void**)&h_prm, h_prm_bytes));
+        }
+        if (h_out_bytes < c * (p() + 1) * sizeof(double)) {
+            if (h_out) cudaFreeHost(h_out);
+            h_out_bytes = c * (p() + 1) * sizeof(double);
+            CUDA_TRY(cudaMallocHost((void**)&h_out, h_out_bytes));
+        }
+        if (h_status_bytes < c * sizeof(int)) {
+            if (h_status) cudaFreeHost(h_status);
+            h_status_bytes = c * sizeof(int);
+            CUDA_TRY(cudaMallocHost((void**)&h_status, h_status_bytes));
+        }
+        cap = newcap;
+        return HBEGP_OK;
+    }
+
+    // theta (ln space) -> clamped natural parameters rounded to T (fit.rs:94-96, matern_kernel.rs:167-179,
+    // constant_kernel.rs:58-62, bounded_value.rs:43-56).  Noise is not clamped.
+    void fill_params(const double* theta, const double* lo, const double* hi, T* out) const {
+        out[0] = (T)std::exp(theta[0]);
+        for (int k = 1; k < p(); k++) {
+            double v = std::exp(theta[k]);
+            if (lo && v < lo[k]) v = lo[k];
+            else if (hi && hi[k] < v) v = hi[k];
+            out[k] = (T)v;
+        }
+    }
+
+    // ---------------------------------------------------------------- recursive Cholesky + inverse
+    int chol_inv(cudaStream_t st, int s0, int cnt, int r0, int s) {
+        T* Ab = (T*)A.p + (size_t)s0 * mstride();
+        T* Wb = (T*)W.p + (size_t)s0 * mstride();
+        if (s == TILE) {
+            k_leaf<T><<<dim3(1, 1, cnt), 256, 0, st>>>(Ab, Wb, mstride(), np, r0, (T*)ldp.p + (size_t)s0 * (np / TILE), np / TILE,
+                                                       (int*)d_status.p + s0);
+            launches++;
+            CUDA_TRY(cudaGetLastError());
+            return HBEGP_OK;
+        }
+        int q = s / TILE, q1 = (q + 1) / 2;
+        if (q >= 4 && (q1 & 1)) q1 += 1;  // keep the large blocks multiples of 128 for the 128x128 GEMM tile
+        if (q1 >= q) q1 = q - 1;
+        const int s1 = q1 * TILE, s2 = s - s1;
+        int rc;
+        if ((rc = chol_inv(st, s0, cnt, r0, s1))) return rc;
+        T* A21 = Ab + (long)(r0 + s1) * np + r0;
+        T* W21 = Wb + (long)(r0 + s1) * np + r0;
+        T* W11 = Wb + (long)r0 * np + r0;
+        T* A22 = Ab + (long)(r0 + s1) * np + r0 + s1;
+        T* W22 = Wb + (long)(r0 + s1) * np + r0 + s1;
+        GemmArgs<T> g{};
+        g.lda = g.ldb = g.ldc = np;
+        g.sA = g.sB = g.sC = mstride();
+        g.rowsumsq = nullptr;
+        // 1. panel solve as a product with the inverse: L21 = A21 W11^T  -> W(2,1)
+        g.A = A21; g.B = W11; g.C = W21; g.M = s2; g.N = s1; g.K = s1; g.kmode = K_LE_N; g.lower_only = 0;
+        g.alpha = T(1); g.beta = T(0);
+        CUDA_TRY((launch_gemm<T, true, true>(g, cnt, st))); launches++;
+        // 2. trailing update: A22 -= L21 L21^T (lower tiles)
+        g.A = W21; g.B = W21; g.C = A22; g.M = s2; g.N = s2; g.K = s1; g.kmode = K_FULL; g.lower_only = 1;
+        g.alpha = T(-1); g.beta = T(1);
+        CUDA_TRY((launch_gemm<T, true, true>(g, cnt, st))); launches++;
+        // 3. T = L21 W11 -> A(2,1)
+        g.A = W21; g.B = W11; g.C = A21; g.M = s2; g.N = s1; g.K = s1; g.kmode = K_GE_N; g.lower_only = 0;
+        g.alpha = T(1); g.beta = T(0);
+        CUDA_TRY((launch_gemm<T, true, false>(g, cnt, st))); launches++;
+        if ((rc = chol_inv(st, s0, cnt, r0 + s1, s2))) return rc;
+        // 4. W21 = -W22 T
+        g.A = W22; g.B = A21; g.C = W21; g.M = s2; g.N = s1; g.K = s2; g.kmode = K_LE_M; g.lower_only = 0;
+        g.alpha = T(-1); g.beta = T(0);
+        CUDA_TRY((launch_gemm<T, true, false>(g, cnt, st))); launches++;
+        return HBEGP_OK;
+    }
+
+    // K^-1 = W^T W on the lower tiles, written over the (dead) Cholesky factor in A
+    int lauum(cudaStream_t st, T* Ab, T* Wb, int cnt) {
+        GemmArgs<T> g{};
+        g.lda = g.ldb = g.ldc = np;
+        g.sA = g.sB = g.sC = mstride();
+        g.A = Wb; g.B = Wb; g.C = Ab; g.M = np; g.N = np; g.K = np; g.kmode = K_GE_M; g.lower_only = 1;
+        g.alpha = T(1); g.beta = T(0);
+        g.rowsumsq = nullptr;
+        CUDA_TRY((launch_gemm<T, false, false>(g, cnt, st))); launches++;
+        return HBEGP_OK;
+    }
+
+    template <int NU2>
+    int pipeline_nu(cudaStream_t st, int s0, int cnt, bool want_grad, bool want_kinv) {
+        T* Ab = (T*)A.p + (size_t)s0 * mstride();
+        T* Wb = (T*)W.p + (size_t)s0 * mstride();
+        T* xs = (T*)xsT.p + (size_t)s0 * d * np;
+        T* pr = (T*)prm.p + (size_t)s0 * p();
+        T* ub = (T*)u.p + (size_t)s0 * np;
+        T* al = (T*)alpha.p + (size_t)s0 * np;
+        T* tp = (T*)tpart.p + (size_t)s0 * nchunks() * np;
+        double* gp = (double*)gpart.p + (size_t)s0 * ntiles_lower() * p();
+        const size_t xsm = 2 * (size_t)d * TILE * sizeof(T);
+        k_scale_x<T><<<dim3((np + 255) / 256, d, cnt), 256, 0, st>>>((const T*)dX.p, (int)n, d, np, pr, p(), xs);
+        launches++;
+        k_assemble<T, NU2><<<dim3(ntiles_lower(), 1, cnt), 256, xsm, st>>>(xs, (int)n, d, np, pr, p(), Ab, mstride());
+        launches++;
+        CUDA_TRY(cudaGetLastError());
+        int rc;
+        if ((rc = chol_inv(st, s0, cnt, 0, np))) return rc;
+        // alpha = W^T (W y)   (lml.rs:54 solves K alpha = y through the factorisation)
+        k_trmv_lower<T><<<dim3(np / 8, 1, cnt), 256, 0, st>>>(Wb, mstride(), np, (const T*)dY.p, 0, ub, np);
+        launches++;
+        k_trmv_lower_t_part<T><<<dim3(np / TILE, nchunks(), cnt), 256, 0, st>>>(Wb, mstride(), np, ub, np, tp, nchunks());
+        launches++;
+        k_sum_chunks<T><<<dim3((np + 255) / 256, 1, cnt), 256, 0, st>>>(tp, nchunks(), np, al, np);
+        launches++;
+        if (want_grad || want_kinv) {
+            if ((rc = lauum(st, Ab, Wb, cnt))) return rc;
+        }
+        if (want_grad) {
+            const size_t gsm = xsm + 2 * TILE * sizeof(T) + 8 * (size_t)p() * sizeof(double);
+            k_grad_contract<T, NU2><<<dim3(ntiles_lower(), 1, cnt), 256, gsm, st>>>(
+                Ab, mstride(), (int)n, d, np, xs, al, np, pr, p(), gp, (long)ntiles_lower() * p());
+            launches++;
+        }
+        k_finish<T><<<cnt, 256, 0, st>>>((const T*)dY.p, al, np, (int)n, np, (T*)ldp.p + (size_t)s0 * (np / TILE), np / TILE, gp,
+                                        (long)ntiles_lower() * p(), ntiles_lower(), p(), (int*)d_status.p + s0,
+                                        (double*)d_lml.p + s0, (double*)d_grad.p + (size_t)s0 * p(), want_grad ? 1 : 0);
+        launches++;
+        CUDA_TRY(cudaGetLastError());
+        return HBEGP_OK;
+    }
+
+    int pipeline(int nu2, cudaStream_t st, int s0, int cnt, bool want_grad, bool want_kinv) {
+        if (nu2 == 5) return pipeline_nu<5>(st, s0, cnt, want_grad, want_kinv);
+        if (nu2 == 3) return pipeline_nu<3>(st, s0, cnt, want_grad, want_kinv);
+        return pipeline_nu<1>(st, s0, cnt, want_grad, want_kinv);
+    }
+
+    // Evaluates `cnt` <= cap parameter sets already staged in h_prm; results land in h_out / h_status.
+    int run_chunk(int nu2, int cnt, bool want_grad, bool want_kinv) {
+        CUDA_TRY(cudaMemcpyAsync(prm.p, h_prm, (size_t)cnt * p() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemsetAsync(d_status.p, 0, (size_t)cnt * sizeof(int), stream));
+        int groups = std::min<int>((int)sub.size(), cnt);
+        // large matrices fill the GPU on their own: keep the batch together so the GEMM grids stay big
+        if (groups <= 1) {
+            int rc = pipeline(nu2, stream, 0, cnt, want_grad, want_kinv);
+            if (rc) return rc;
+        } else {
+            CUDA_TRY(cudaEventRecord(fork_ev, stream));
+            int base = cnt / groups, extra = cnt % groups, s0 = 0;
+            for (int g = 0; g < groups; g++) {
+                int c = base + (g < extra ? 1 : 0);
+                CUDA_TRY(cudaStreamWaitEvent(sub[g], fork_ev, 0));
+                int rc = pipeline(nu2, sub[g], s0, c, want_grad, want_kinv);
+                if (rc) return rc;
+                CUDA_TRY(cudaEventRecord(sub_done[g], sub[g]));
+                CUDA_TRY(cudaStreamWaitEvent(stream, sub_done[g], 0));
+                s0 += c;
+            }
+        }
+        CUDA_TRY(cudaMemcpyAsync(h_out, d_lml.p, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (want_grad)
+            CUDA_TRY(cudaMemcpyAsync(h_out + cap, d_grad.p, (size_t)cnt * p() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(h_status, d_status.p, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        return HBEGP_OK;
+    }
+
+    int eval_batch(double nu, int B, const double* theta, const double* lo, const double* hi, double* lml, double* grad,
+                   int* status) override {
+        int nu2, rc;
+        if ((rc = nu_to_nu2(nu, &nu2))) return rc;
+        if (B < 0 || (B > 0 && (!theta || !lml))) return fail(HBEGP_ERR_INVALID, "lml_grad_batch: bad arguments");
+        if (B == 0) return HBEGP_OK;
+        CUDA_TRY(cudaSetDevice(device));
+        if ((rc = ensure_capacity(B))) return rc;
+        for (int b0 = 0; b0 < B; b0 += cap) {
+            int cnt = std::min(cap, B - b0);
+            for (int b = 0; b < cnt; b++) fill_params(theta + (size_t)(b0 + b) * p(), lo, hi, h_prm + (size_t)b * p());
+            if ((rc = run_chunk(nu2, cnt, grad != nullptr, false))) return rc;
+            for (int b = 0; b < cnt; b++) {
+                bool bad = h_status[b] != 0 || !std::isfinite(h_out[b]);
+                lml[b0 + b] = bad ? -std::numeric_limits<double>::infinity() : h_out[b];
+                if (status) status[b0 + b] = bad ? HBEGP_NOT_PD : HBEGP_OK;
+                if (grad)
+                    for (int k = 0; k < p(); k++) grad[(size_t)(b0 + b) * p() + k] = bad ? 0.0 : h_out[cap + (size_t)b * p() + k];
+            }
+        }
+        return HBEGP_OK;
+    }
+
+    int model_create(double nu, const double* theta, const double* lo, const double* hi, Model** out, double* lml,
+                     void* alpha_out, void* kinv_out) override;
+
+    int debug_factor(double nu, const double* theta, void* k, void* w, void* kinv, int* status) override {
+        int nu2, rc;
+        if ((rc = nu_to_nu2(nu, &nu2))) return rc;
+        CUDA_TRY(cudaSetDevice(device));
+        if ((rc = ensure_capacity(1))) return rc;
+        fill_params(theta, nullptr, nullptr, h_prm);
+        CUDA_TRY(cudaMemcpyAsync(prm.p, h_prm, (size_t)p() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemsetAsync(d_status.p, 0, sizeof(int), stream));
+        DevBuf tmp;
+        if ((rc = tmp.ensure((size_t)n * n * sizeof(T)))) return rc;
+        dim3 fg((unsigned)((n + 255) / 256), (unsigned)n);
+        const size_t xsm = 2 * (size_t)d * TILE * sizeof(T);
+        auto copy_out = [&](const T* src, void* dst, int mode) -> int {
+            k_sym_fill<T><<<fg, 256, 0, stream>>>(src, np, (int)n, (T*)tmp.p, mode);
+            CUDA_TRY(cudaMemcpyAsync(dst, tmp.p, (size_t)n * n * sizeof(T), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            return HBEGP_OK;
+        };
+        k_scale_x<T><<<dim3((np + 255) / 256, d, 1), 256, 0, stream>>>((const T*)dX.p, (int)n, d, np, (T*)prm.p, p(), (T*)xsT.p);
+        if (nu2 == 5) k_assemble<T, 5><<<dim3(ntiles_lower(), 1, 1), 256, xsm, stream>>>((T*)xsT.p, (int)n, d, np, (T*)prm.p, p(), (T*)A.p, mstride());
+        else if (nu2 == 3) k_assemble<T, 3><<<dim3(ntiles_lower(), 1, 1), 256, xsm, stream>>>((T*)xsT.p, (int)n, d, np, (T*)prm.p, p(), (T*)A.p, mstride());
+        else k_assemble<T, 1><<<dim3(ntiles_lower(), 1, 1), 256, xsm, stream>>>((T*)xsT.p, (int)n, d, np, (T*)prm.p, p(), (T*)A.p, mstride());
+        CUDA_TRY(cudaGetLastError());
+        if (k && (rc = copy_out((T*)A.p, k, 1))) { tmp.release(); return rc; }
+        if ((rc = chol_inv(stream, 0, 1, 0, np))) { tmp.release(); return rc; }
+        if (w && (rc = copy_out((T*)W.p, w, 1))) { tmp.release(); return rc; }
+        if (kinv) {
+            if ((rc = lauum(stream, (T*)A.p, (T*)W.p, 1))) { tmp.release(); return rc; }
+            if ((rc = copy_out((T*)A.p, kinv, 0))) { tmp.release(); return rc; }
+        }
+        int hs = 0;
+        CUDA_TRY(cudaMemcpyAsync(&hs, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (status) *status = hs ? HBEGP_NOT_PD : HBEGP_OK;
+        tmp.release();
+        return HBEGP_OK;
+    }
+};
+
+template <typename T>
+struct ModelT : Model {
+    int predict_chunk_rows() const {
+        size_t budget = (size_t)1 << 30;  // k* chunk of at most 1 GiB
+        long rows = (long)(budget / ((size_t)np * sizeof(T)));
+        rows = std::max<long>(128, rows / 128 * 128);
+        return (int)std::min<long>(rows, 1 << 16);
+    }
+
+    template <int NU2>
+    int predict_impl(long m, const T* xs, T* mean, T* var, unsigned long long* nb) {
+        Engine<T>* e = static_cast<Engine<T>*>(eng);
+        cudaStream_t st = e->stream;
+        const size_t ksm = (2 * (size_t)d * TILE + TILE) * sizeof(T);
+        if (ksm > 48 * 1024) {
+            static bool done = false;
+            if (!done) {
+                CUDA_TRY(cudaFuncSetAttribute(k_kstar_mean<T, NU2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksm));
+                done = true;
+            }
+        }
+        if (var == nullptr) {
+            long rows = round_up(m, TILE);
+            k_kstar_mean<T, NU2><<<(unsigned)(rows / TILE), 256, ksm, st>>>(xs, m, 0, d, (const T*)xsT.p, (int)n, np, (const T*)ls.p,
+                                                                           (T)c, (const T*)alpha.p, nullptr, mean);
+            e->launches++;
+            CUDA_TRY(cudaGetLastError());
+            return HBEGP_OK;
+        }
+        const int chunk = (int)std::min<long>(predict_chunk_rows(), round_up(m, 128));
+        const int bn = (np % 128 == 0) ? 128 : 64;
+        const int ntile = np / bn;
+        int rc;
+        if ((rc = kstar.ensure((size_t)chunk * np * sizeof(T)))) return rc;
+        if ((rc = part.ensure((size_t)chunk * ntile * sizeof(T)))) return rc;
+        for (long row0 = 0; row0 < m; row0 += chunk) {
+            const int rows = (int)std::min<long>(chunk, round_up(m - row0, 128));
+            k_kstar_mean<T, NU2><<<rows / TILE, 256, ksm, st>>>(xs, m, row0, d, (const T*)xsT.p, (int)n, np, (const T*)ls.p, (T)c,
+                                                               (const T*)alpha.p, (T*)kstar.p, mean);
+            e->launches++;
+            // |W k*|^2 per candidate: U = k* W^T restricted to k <= column tile, squared and row-summed in the epilogue
+            GemmArgs<T> g{};
+            g.A = (const T*)kstar.p; g.lda = np; g.sA = 0;
+            g.B = (const T*)W.p; g.ldb = np; g.sB = 0;
+            g.C = nullptr; g.ldc = 0; g.sC = 0;
+            g.M = rows; g.N = np; g.K = np; g.kmode = K_LE_N; g.lower_only = 0;
+            g.alpha = T(1); g.beta = T(0);
+            g.rowsumsq = (T*)part.p; g.ld_rs = ntile; g.s_rs = 0;
+            CUDA_TRY((launch_gemm<T, true, true>(g, 1, st, bn)));
+            e->launches++;
+            k_var_finish<T><<<(rows + 255) / 256, 256, 0, st>>>((const T*)part.p, ntile, ntile, rows, m, row0, (T)c, var, nb);
+            e->launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+        return HBEGP_OK;
+    }
+
+    int predict_device(long m, const void* xs, void* mean, void* var, long* n_below_device) override {
+        if (m < 0 || (m > 0 && (!xs || !mean))) return fail(HBEGP_ERR_INVALID, "predict: bad arguments");
+        if (m == 0) return HBEGP_OK;
+        Engine<T>* e = static_cast<Engine<T>*>(eng);
+        CUDA_TRY(cudaSetDevice(e->device));
+        int rc;
+        if ((rc = nbelow.ensure(sizeof(unsigned long long)))) return rc;
+        unsigned long long* nb = n_below_device ? (unsigned long long*)n_below_device : (unsigned long long*)nbelow.p;
+        if (var) CUDA_TRY(cudaMemsetAsync(nb, 0, sizeof(unsigned long long), e->stream));
+        if (nu2 == 5) return predict_impl<5>(m, (const T*)xs, (T*)mean, (T*)var, nb);
+        if (nu2 == 3) return predict_impl<3>(m, (const T*)xs, (T*)mean, (T*)var, nb);
+        return predict_impl<1>(m, (const T*)xs, (T*)mean, (T*)var, nb);
+    }
+
+    int predict_host(long m, const void* xs, void* mean, void* var, long* n_below) override {
+        if (m < 0 || (m > 0 && (!xs || !mean))) return fail(HBEGP_ERR_INVALID, "predict: bad arguments");
+        if (n_below) *n_below = 0;
+        if (m == 0) return HBEGP_OK;
+        Engine<T>* e = static_cast<Engine<T>*>(eng);
+        CUDA_TRY(cudaSetDevice(e->device));
+        int rc;
+        if ((rc = xs_tmp.ensure((size_t)m * d * sizeof(T)))) return rc;
+        if ((rc = mean_tmp.ensure((size_t)m * sizeof(T)))) return rc;
+        if (var && (rc = var_tmp.ensure((size_t)m * sizeof(T)))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(xs_tmp.p, xs, (size_t)m * d * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+        if ((rc = predict_device(m, xs_tmp.p, mean_tmp.p, var ? var_tmp.p : nullptr, nullptr))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(mean, mean_tmp.p, (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, e->stream));
+        unsigned long long hb = 0;
+        if (var) {
+            CUDA_TRY(cudaMemcpyAsync(var, var_tmp.p, (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, e->stream));
+            CUDA_TRY(cudaMemcpyAsync(&hb, nbelow.p, sizeof(hb), cudaMemcpyDeviceToHost, e->stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        if (n_below) *n_below = (long)hb;
+        return HBEGP_OK;
+    }
+};
+
+template <typename T>
+int Engine<T>::model_create(double nu, const double* theta, const double* lo, const double* hi, Model** out, double* lml,
+                            void* alpha_out, void* kinv_out) {
+    int nu2, rc;
+    if ((rc = nu_to_nu2(nu, &nu2))) return rc;
+    if (!theta || !out) return fail(HBEGP_ERR_INVALID, "model_create: bad arguments");
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(device));
+    if ((rc = ensure_capacity(1))) return rc;
+    fill_params(theta, lo, hi, h_prm);
+    const bool want_kinv = kinv_out != nullptr;
+    if ((rc = run_chunk(nu2, 1, false, want_kinv))) return rc;
+    if (h_status[0] != 0 || !std::isfinite(h_out[0]))
+        return fail(HBEGP_NOT_PD, "Kernel matrix must be invertible. (fit.rs:55)");
+    if (lml) *lml = h_out[0];
+    ModelT<T>* m = new ModelT<T>();
+    m->eng = this;
+    m->dtype = dtype;
+    m->n = n;
+    m->d = d;
+    m->np = np;
+    m->nu2 = nu2;
+    m->c = (double)h_prm[1];
+    auto bail = [&](int code) { delete m; return code; };
+    if ((rc = m->W.ensure((size_t)np * np * sizeof(T)))) return bail(rc);
+    if ((rc = m->alpha.ensure((size_t)np * sizeof(T)))) return bail(rc);
+    if ((rc = m->xsT.ensure((size_t)d * np * sizeof(T)))) return bail(rc);
+    if ((rc = m->ls.ensure((size_t)d * sizeof(T)))) return bail(rc);
+    cudaError_t ce;
+    ce = cudaMemcpyAsync(m->W.p, W.p, (size_t)np * np * sizeof(T), cudaMemcpyDeviceToDevice, stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(m->alpha.p, alpha.p, (size_t)np * sizeof(T), cudaMemcpyDeviceToDevice, stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(m->xsT.p, xsT.p, (size_t)d * np * sizeof(T), cudaMemcpyDeviceToDevice, stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(m->ls.p, (T*)prm.p + 2, (size_t)d * sizeof(T), cudaMemcpyDeviceToDevice, stream);
+    if (ce == cudaSuccess && alpha_out) ce = cudaMemcpyAsync(alpha_out, alpha.p, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, stream);
+    if (ce != cudaSuccess) { delete m; return fail(HBEGP_ERR_CUDA, std::string("model_create copy: ") + cudaGetErrorString(ce)); }
+    if (kinv_out) {
+        DevBuf tmp;
+        if ((rc = tmp.ensure((size_t)n * n * sizeof(T)))) return bail(rc);
+        dim3 fg((unsigned)((n + 255) / 256), (unsigned)n);
+        k_sym_fill<T><<<fg, 256, 0, stream>>>((const T*)A.p, np, (int)n, (T*)tmp.p, 0);
+        launches++;
+        ce = cudaMemcpyAsync(kinv_out, tmp.p, (size_t)n * n * sizeof(T), cudaMemcpyDeviceToHost, stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream);
+        tmp.release();
+        if (ce != cudaSuccess) { delete m; return fail(HBEGP_ERR_CUDA, std::string("model_create kinv: ") + cudaGetErrorString(ce)); }
+    }
+    ce = cudaStreamSynchronize(stream);
+    if (ce != cudaSuccess) { delete m; return fail(HBEGP_ERR_CUDA, std::string("model_create: ") + cudaGetErrorString(ce)); }
+    models.push_back(m);
+    *out = m;
+    return HBEGP_OK;
+}
+
+// ------------------------------------------------------------------------------------ restart loop
+static int fit_runs_impl(EngineBase* e, double nu, int n_runs, const double* starts, const double* blo, const double* bhi,
+                         int maxeval, hbegp_run_result* results, double* best_theta) {
+    const int p = e->d + 2;
+    if (n_runs < 0 || (n_runs > 0 && (!starts || !blo || !bhi || !results || !best_theta)))
+        return fail(HBEGP_ERR_INVALID, "fit_runs: bad arguments");
+    std::vector<double> lb(p), ub(p);
+    for (int k = 0; k < p; k++) {
+        if (!(blo[k] > 0) || !(bhi[k] >= blo[k])) return fail(HBEGP_ERR_INVALID, "fit_runs: bounds must satisfy 0 < lo <= hi");
+        lb[k] = std::log(blo[k]);  // fit.rs:140, kernel.bounds()
+        ub[k] = std::log(bhi[k]);
+    }
+    std::vector<BoundedLbfgs> opt;
+    opt.reserve(n_runs);
+    for (int r = 0; r < n_runs; r++) {
+        opt.emplace_back(p, starts + (size_t)r * p, lb.data(), ub.data(), maxeval);
+        results[r].best_lml = -std::numeric_limits<double>::infinity();
+        results[r].best_eval = -1;
+        results[r].n_evals = 0;
+        results[r].final_f = std::numeric_limits<double>::infinity();
+        results[r].status = HBEGP_NOT_PD;
+        results[r].reserved = 0;
+        for (int k = 0; k < p; k++) best_theta[(size_t)r * p + k] = starts[(size_t)r * p + k];
+    }
+    std::vector<int> live;
+    std::vector<double> th, lml, grad;
+    std::vector<int> st;
+    for (;;) {
+        live.clear();
+        for (int r = 0; r < n_runs; r++)
+            if (!opt[r].done()) live.push_back(r);
+        if (live.empty()) break;
+        const int B = (int)live.size();
+        th.resize((size_t)B * p);
+        lml.resize(B);
+        grad.resize((size_t)B * p);
+        st.resize(B);
+        for (int b = 0; b < B; b++) std::memcpy(&th[(size_t)b * p], opt[live[b]].ask(), sizeof(double) * p);
+        int rc = e->eval_batch(nu, B, th.data(), blo, bhi, lml.data(), grad.data(), st.data());
+        if (rc) return rc;
+        for (int b = 0; b < B; b++) {
+            const int r = live[b];
+            hbegp_run_result& R = results[r];
+            const bool ok = st[b] == HBEGP_OK;
+            // capture rule of fit.rs:115-125: first success, then strictly larger LML only
+            if (ok && (R.best_eval < 0 || lml[b] > R.best_lml)) {
+                R.best_lml = lml[b];
+                R.best_eval = R.n_evals;
+                R.status = HBEGP_OK;
+                std::memcpy(&best_theta[(size_t)r * p], &th[(size_t)b * p], sizeof(double) * p);
+            }
+            R.n_evals++;
+            double f = ok ? -lml[b] : std::numeric_limits<double>::infinity();
+            for (int k = 0; k < p; k++) grad[(size_t)b * p + k] = ok ? -grad[(size_t)b * p + k] : 0.0;
+            opt[r].tell(f, &grad[(size_t)b * p]);
+            if (opt[r].done()) R.final_f = opt[r].f();
+        }
+    }
+    return HBEGP_OK;
+}
+
+}  // namespace hbegp
+
+// =================================================================================== C ABI
+using namespace hbegp;
+
+struct hbegp_ctx {
+    EngineBase* eng;
+};
+struct hbegp_model {
+    Model* m;
+};
+
+extern "C" {
+
+const char* hbegp_version(void) { return "hbegp 0.1.0 (sm_100a)"; }
+const char* hbegp_last_error(void) { return g_last_error.c_str(); }
+
+int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
+    if (!out) return fail(HBEGP_ERR_INVALID, "ctx_create: out is null");
+    *out = nullptr;
+    if (dtype != HBEGP_F64 && dtype != HBEGP_F32) return fail(HBEGP_ERR_INVALID, "ctx_create: dtype must be HBEGP_F64 or HBEGP_F32");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(HBEGP_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(ce));
+    if (device < 0 || device >= ndev) return fail(HBEGP_ERR_INVALID, "ctx_create: bad device index");
+    CUDA_TRY(cudaSetDevice(device));
+    EngineBase* e = (dtype == HBEGP_F64) ? static_cast<EngineBase*>(new Engine<double>()) : static_cast<EngineBase*>(new Engine<float>());
+    e->device = device;
+    e->dtype = dtype;
+    if (stream) {
+        e->stream = (cudaStream_t)stream;
+    } else {
+        ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+        if (ce != cudaSuccess) { delete e; return fail(HBEGP_ERR_CUDA, cudaGetErrorString(ce)); }
+        e->own_stream = true;
+    }
+    int nsub = 4;
+    if (const char* s = getenv("HBEGP_STREAMS")) nsub = std::max(1, std::min(16, atoi(s)));
+    for (int i = 0; i < nsub; i++) {
+        cudaStream_t s;
+        cudaEvent_t ev;
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+            delete e;
+            return fail(HBEGP_ERR_CUDA, "ctx_create: could not create streams");
+        }
+        e->sub.push_back(s);
+        e->sub_done.push_back(ev);
+    }
+    if (cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming) != cudaSuccess) { delete e; return fail(HBEGP_ERR_CUDA, "ctx_create: event"); }
+    *out = new hbegp_ctx{e};
+    return HBEGP_OK;
+}
+
+int hbegp_ctx_destroy(hbegp_ctx* ctx) {
+    if (!ctx) return HBEGP_OK;
+    EngineBase* e = ctx->eng;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (Model* m : e->models) {  // models outliving their context keep answering with HBEGP_ERR_INVALID
+        m->release_all();
+        m->eng = nullptr;
+    }
+    e->models.clear();
+    for (auto s : e->sub) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    for (auto ev : e->sub_done) cudaEventDestroy(ev);
+    if (e->fork_ev) cudaEventDestroy(e->fork_ev);
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+    delete e;
+    delete ctx;
+    return HBEGP_OK;
+}
+
+int hbegp_ctx_set_workspace_limit(hbegp_ctx* ctx, unsigned long long bytes) {
+    if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");
+    ctx->eng->ws_limit = (size_t)bytes;
+    return HBEGP_OK;
+}
+
+long long hbegp_ctx_launch_count(hbegp_ctx* ctx) { return ctx ? ctx->eng->launches : 0; }
+
+int hbegp_set_data(hbegp_ctx* ctx, long n, int d, const void* x, const void* y) {
+    if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");
+    return ctx->eng->set_data(n, d, x, y, false);
+}
+int hbegp_set_data_device(hbegp_ctx* ctx, long n, int d, const void* x, const void* y) {
+    if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");
+    return ctx->eng->set_data(n, d, x, y, true);
+}
+
+int hbegp_lml_grad_batch(hbegp_ctx* ctx, double nu, int B, const double* theta, const double* lo, const double* hi,
+                         double* lml, double* grad, int* status) {
+    if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");
+    return ctx->eng->eval_batch(nu, B, theta, lo, hi, lml, grad, status);
+}
+
+int hbegp_fit_runs(hbegp_ctx* ctx, double nu, int n_runs, const double* starts, const double* bounds_lo,
+                   const double* bounds_hi, int maxeval, hbegp_run_result* results, double* best_theta) {
+    if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");
+    if (ctx->eng->n <= 0) return fail(HBEGP_ERR_INVALID, "no training data: call hbegp_set_data first");
+    return fit_runs_impl(ctx->eng, nu, n_runs, starts, bounds_lo, bounds_hi, maxeval, results, best_theta);
+}
+
+int hbegp_pick_best_run(int n_runs, const hbegp_run_result* results) {
+    int best = -1;
+    for (int r = 0; r < n_runs; r++) {
+        if (results[r].status != HBEGP_OK || results[r].best_eval < 0) continue;
+        if (best < 0 || results[r].best_lml > results[best].best_lml) best = r;
+    }
+    return best;
+}
+
+int hbegp_model_create(hbegp_ctx* ctx, double nu, const double* theta, const double* lo, const double* hi,
+                       hbegp_model** out, double* lml, void* alpha_out, void* kinv_out) {
+    if (!ctx || !out) return fail(HBEGP_ERR_INVALID, "null context / out");
+    Model* m = nullptr;
+    int rc = ctx->eng->model_create(nu, theta, lo, hi, &m, lml, alpha_out, kinv_out);
+    *out = nullptr;
+    if (rc) return rc;
+    *out = new hbegp_model{m};
+    return HBEGP_OK;
+}
+
+int hbegp_model_destroy(hbegp_model* model) {
+    if (!model) return HBEGP_OK;
+    if (model->m) {
+        if (model->m->eng) {
+            cudaSetDevice(model->m->eng->device);
+            cudaStreamSynchronize(model->m->eng->stream);
+        }
+        delete model->m;
+    }
+    delete model;
+    return HBEGP_OK;
+}
+
+long hbegp_model_n(const hbegp_model* model) { return model ? model->m->n : 0; }
+int hbegp_model_dim(const hbegp_model* model) { return model ? model->m->d : 0; }
+
+int hbegp_predict(hbegp_model* model, long m, const void* xs, void* mean, void* var, long* n_below_warn) {
+    if (!model) return fail(HBEGP_ERR_INVALID, "null model");
+    if (!model->m->eng) return fail(HBEGP_ERR_INVALID, "the model's context has been destroyed");
+    return model->m->predict_host(m, xs, mean, var, n_below_warn);
+}
+
+int hbegp_predict_device(hbegp_model* model, long m, const void* xs_device, void* mean_device, void* var_device,
+                         long* n_below_warn_device) {
+    if (!model) return fail(HBEGP_ERR_INVALID, "null model");
+    if (!model->m->eng) return fail(HBEGP_ERR_INVALID, "the model's context has been destroyed");
+    return model->m->predict_device(m, xs_device, mean_device, var_device, n_below_warn_device);
+}
+
+int hbegp_minimize_by_gradient(hbegp_objective_fn objective, void* user, int n, double* x, const double* lo,
+                               const double* hi, int maxeval, double* f_out) {
+    if (!objective || !x || !lo || !hi || n <= 0) return fail(HBEGP_ERR_INVALID, "minimize_by_gradient: bad arguments");
+    BoundedLbfgs opt(n, x, lo, hi, maxeval);
+    std::vector<double> g(n);
+    while (!opt.done()) {
+        double f = objective(opt.ask(), g.data(), user);
+        opt.tell(f, g.data());
+    }
+    std::memcpy(x, opt.x(), sizeof(double) * n);
+    if (f_out) *f_out = opt.f();
+    return opt.evals();
+}
+
+void hbegp_rng_seed(unsigned long long seed, unsigned long long state[4]) { Xoshiro256::seed(seed, state); }
+
+void hbegp_rng_fork(unsigned long long state[4], unsigned long long child[4]) {
+    Xoshiro256 r;
+    std::memcpy(r.s, state, sizeof(r.s));
+    for (int i = 0; i < 4; i++) child[i] = r.next();
+    std::memcpy(state, r.s, sizeof(r.s));
+    if (!(child[0] | child[1] | child[2] | child[3])) Xoshiro256::seed(0, child);
+}
+
+double hbegp_rng_uniform(unsigned long long state[4], double lo, double hi) {
+    Xoshiro256 r;
+    std::memcpy(r.s, state, sizeof(r.s));
+    double v = r.uniform_inclusive(lo, hi);
+    std::memcpy(state, r.s, sizeof(r.s));
+    return v;
+}
+
+int hbegp_debug_factor(hbegp_ctx* ctx, double nu, const double* theta, void* k, void* w, void* kinv, int* status) {
+    if (!ctx || !theta) return fail(HBEGP_ERR_INVALID, "debug_factor: bad arguments");
+    if (ctx->eng->n <= 0) return fail(HBEGP_ERR_INVALID, "no training data: call hbegp_set_data first");
+    return ctx->eng->debug_factor(nu, theta, k, w, kinv, status);
+}
+
+}  // extern "C"

@@ -1,0 +1,527 @@
+// Non-GEMM kernels of the GP hot path (sm_100a): kernel-matrix assembly, the 64x64 Cholesky+inverse
+// leaf, triangular matrix-vector products, the fused LML-gradient contraction, the reductions that
+// finish an evaluation, and the prediction kernels.  All matrices are row-major with leading dimension
+// Np = n rounded up to a multiple of 64; the padding block is the identity, which keeps every tile full
+// (Cholesky, inverse and log-determinant of diag(K, I) are those of K).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace hbegp {
+
+constexpr int TILE = 64;  // leaf / tile edge
+
+// Per-evaluation hyper-parameters, already clamped and rounded to T on the host
+// (src/gpr/fit.rs:94-96): prm[0] = noise, prm[1] = c, prm[2 + k] = l_k.
+template <typename T>
+__device__ __forceinline__ T dev_exp(T x);
+template <>
+__device__ __forceinline__ double dev_exp<double>(double x) { return exp(x); }
+template <>
+__device__ __forceinline__ float dev_exp<float>(float x) { return expf(x); }
+template <typename T>
+__device__ __forceinline__ T dev_sqrt(T x);
+template <>
+__device__ __forceinline__ double dev_sqrt<double>(double x) { return sqrt(x); }
+template <>
+__device__ __forceinline__ float dev_sqrt<float>(float x) { return sqrtf(x); }
+template <typename T>
+__device__ __forceinline__ T dev_log(T x);
+template <>
+__device__ __forceinline__ double dev_log<double>(double x) { return log(x); }
+template <>
+__device__ __forceinline__ float dev_log<float>(float x) { return logf(x); }
+
+// Matern correlation from the scaled distance r (src/gpr/matern_kernel.rs:65-80).  NU2 = 2 * nu.
+template <typename T, int NU2>
+__device__ __forceinline__ T matern_corr(T r) {
+    if (NU2 == 1) return dev_exp<T>(-r);
+    if (NU2 == 3) {
+        T k = r * T(1.7320508075688772935);
+        return (k + T(1)) * dev_exp<T>(-k);
+    }
+    T k = r * T(2.2360679774997896964);
+    return (T(1) + k + k * k / T(3)) * dev_exp<T>(-k);
+}
+
+// lower-triangle tile enumeration: t -> (mt >= nt)
+__device__ __forceinline__ void lower_tile(int t, int& mt, int& nt) {
+    int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while ((long)(r + 1) * (r + 2) / 2 <= t) ++r;
+    while ((long)r * (r + 1) / 2 > t) --r;
+    mt = r;
+    nt = t - r * (r + 1) / 2;
+}
+
+// xsT[b][k][i] = x[i][k] / l_k (division first, matern_kernel.rs:51-60); rows i >= n are zero.
+template <typename T>
+__global__ void k_scale_x(const T* __restrict__ x, int n, int d, int np, const T* __restrict__ prm, int pstride,
+                          T* __restrict__ xsT) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = blockIdx.y, b = blockIdx.z;
+    if (i >= np) return;
+    T l = prm[(long)b * pstride + 2 + k];
+    T v = (i < n) ? x[(long)i * d + k] / l : T(0);
+    xsT[((long)b * d + k) * np + i] = v;
+}
+
+// K = c * matern(|xs_i - xs_j|) + noise * I on the lower tiles (diagonal tiles written in full).
+template <typename T, int NU2>
+__global__ void __launch_bounds__(256) k_assemble(const T* __restrict__ xsT, int n, int d, int np,
+                                                  const T* __restrict__ prm, int pstride, T* __restrict__ K,
+                                                  long kstride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* xi = reinterpret_cast<T*>(smem_raw);  // [d][64]
+    T* xj = xi + d * TILE;
+    int mt, nt;
+    lower_tile(blockIdx.x, mt, nt);
+    const int b = blockIdx.z;
+    const int i0 = mt * TILE, j0 = nt * TILE;
+    const T* xb = xsT + (long)b * d * np;
+    for (int e = threadIdx.x; e < d * TILE; e += 256) {
+        int k = e / TILE, r = e % TILE;
+        xi[e] = xb[(long)k * np + i0 + r];
+        xj[e] = xb[(long)k * np + j0 + r];
+    }
+    __syncthreads();
+    const T noise = prm[(long)b * pstride + 0], c = prm[(long)b * pstride + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    T acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[a][q] = T(0);
+    for (int k = 0; k < d; k++) {
+        T vi[4], vj[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) vi[a] = xi[k * TILE + ty + 16 * a];
+#pragma unroll
+        for (int q = 0; q < 4; q++) vj[q] = xj[k * TILE + tx + 16 * q];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                T df = vi[a] - vj[q];
+                acc[a][q] += df * df;
+            }
+    }
+    T* Kb = K + (long)b * kstride;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            int gi = i0 + ty + 16 * a, gj = j0 + tx + 16 * q;
+            T v;
+            if (gi >= n || gj >= n) v = (gi == gj) ? T(1) : T(0);
+            else {
+                v = c * matern_corr<T, NU2>(dev_sqrt<T>(acc[a][q]));
+                if (gi == gj) v += noise;
+            }
+            Kb[(long)gi * np + gj] = v;
+        }
+}
+
+// Leaf of the recursive factorisation: 64x64 diagonal block at (r0, r0).  In: A block (lower part).
+// Out: L in the lower part of the A block, W = L^-1 as a full tile (zeros above the diagonal) in the
+// W buffer, sum_i ln L_ii in ldp[b][leaf], status[b] = 1 when a pivot is not positive (lml.rs:47-50).
+template <typename T>
+__global__ void __launch_bounds__(256) k_leaf(T* __restrict__ A, T* __restrict__ W, long mstride, int np, int r0,
+                                              T* __restrict__ ldp, int ldp_stride, int* __restrict__ status) {
+    __shared__ T a[TILE][TILE + 1];
+    __shared__ T dinv[TILE];
+    __shared__ int fail;
+    const int b = blockIdx.z, tid = threadIdx.x;
+    T* Ab = A + (long)b * mstride + (long)r0 * np + r0;
+    T* Wb = W + (long)b * mstride + (long)r0 * np + r0;
+    if (tid == 0) fail = 0;
+    for (int e = tid; e < TILE * TILE; e += 256) {
+        int i = e / TILE, j = e % TILE;
+        a[i][j] = (j <= i) ? Ab[(long)i * np + j] : T(0);
+    }
+    // --- right-looking Cholesky; column j stays unscaled in the lower part, L goes to the upper part
+    //     transposed (a[j][i] = L[i][j]) so that one barrier per column suffices.
+    for (int j = 0; j < TILE; j++) {
+        __syncthreads();
+        T dj = a[j][j];
+        if (!(dj > T(0)) || !(dj <= T(1e300))) {
+            if (tid == 0) fail = 1;
+            dj = T(1);
+        }
+        const T rs = T(1) / dev_sqrt<T>(dj);
+        const T rd = T(1) / dj;
+        // trailing update of the cells (i, k) with j < k <= i
+        const int rem = TILE - 1 - j;  // rows j+1 .. 63
+        const int cells = rem * (rem + 1) / 2;
+        for (int e = tid; e < cells; e += 256) {
+            int ii = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+            while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
+            while (ii * (ii + 1) / 2 > e) --ii;
+            int kk = e - ii * (ii + 1) / 2;
+            int i = j + 1 + ii, k = j + 1 + kk;
+            a[i][k] -= a[i][j] * a[k][j] * rd;
+        }
+        if (tid < TILE) {
+            if (tid > j) a[j][tid] = a[tid][j] * rs;  // L[tid][j]
+            if (tid == j) dinv[j] = rs;               // 1 / L[j][j]
+        }
+    }
+    __syncthreads();
+    // --- the lower part is dead now: write L back, then reuse it (with the diagonal) for W = L^-1
+    for (int e = tid; e < TILE * TILE; e += 256) {
+        int i = e / TILE, j = e % TILE;
+        if (j < i) Ab[(long)i * np + j] = a[j][i];
+        else if (j == i) Ab[(long)i * np + j] = T(1) / dinv[i];
+    }
+    __syncthreads();
+    for (int e = tid; e < TILE * TILE; e += 256) {
+        int i = e / TILE, j = e % TILE;
+        if (j <= i) a[i][j] = (i == j) ? T(1) : T(0);
+    }
+    __syncthreads();
+    // --- Gauss-Jordan on [L | I]: rows i > k: W[i][j] -= L[i][k] * (W[k][j] / L[k][k]), j <= k.
+    //     L[i][k] = a[k][i] (upper part), W[i][j] = a[i][j] (lower part); row k is scaled at the end.
+    for (int k = 0; k < TILE - 1; k++) {
+        const T rk = dinv[k];
+        const int rows = TILE - 1 - k, cols = k + 1;
+        for (int e = tid; e < rows * cols; e += 256) {
+            int i = k + 1 + e / cols, j = e % cols;
+            a[i][j] -= a[k][i] * (a[k][j] * rk);
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < TILE * TILE; e += 256) {
+        int i = e / TILE, j = e % TILE;
+        Wb[(long)i * np + j] = (j <= i) ? a[i][j] * dinv[i] : T(0);
+    }
+    if (tid < 32) {
+        T s = T(0);
+        for (int i = tid; i < TILE; i += 32) s += -dev_log<T>(dinv[i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (tid == 0) {
+            ldp[(long)b * ldp_stride + r0 / TILE] = s;
+            if (fail) status[b] = 1;
+        }
+    }
+}
+
+// u[i] = sum_{k <= i} W[i][k] v[k]   (one warp per row)
+template <typename T>
+__global__ void __launch_bounds__(256) k_trmv_lower(const T* __restrict__ W, long mstride, int np,
+                                                    const T* __restrict__ v, long vstride, T* __restrict__ u,
+                                                    long ustride) {
+    const int b = blockIdx.z;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= np) return;
+    const T* wr = W + (long)b * mstride + (long)row * np;
+    const T* vb = v + (long)b * vstride;
+    T s = T(0);
+    for (int k = lane; k <= row; k += 32) s += wr[k] * vb[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) u[(long)b * ustride + row] = s;
+}
+
+// part[b][rc][j] = sum over rows i of chunk rc (256 rows), i >= j, of W[i][j] u[i]
+template <typename T>
+__global__ void __launch_bounds__(256) k_trmv_lower_t_part(const T* __restrict__ W, long mstride, int np,
+                                                           const T* __restrict__ u, long ustride,
+                                                           T* __restrict__ part, int nchunks) {
+    __shared__ T red[4][TILE];
+    const int b = blockIdx.z, jb = blockIdx.x, rc = blockIdx.y;
+    const int tx = threadIdx.x & 63, ph = threadIdx.x >> 6;
+    const int j = jb * TILE + tx;
+    const int rbeg = rc * 256, rend = min(np, rbeg + 256);
+    T s = T(0);
+    if (rend > jb * TILE) {
+        const T* Wb = W + (long)b * mstride;
+        const T* ub = u + (long)b * ustride;
+        for (int i = max(rbeg, jb * TILE) + ph; i < rend; i += 4)
+            if (i >= j) s += Wb[(long)i * np + j] * ub[i];
+    }
+    red[ph][tx] = s;
+    __syncthreads();
+    if (ph == 0) part[((long)b * nchunks + rc) * np + j] = ((red[0][tx] + red[1][tx]) + red[2][tx]) + red[3][tx];
+}
+
+template <typename T>
+__global__ void k_sum_chunks(const T* __restrict__ part, int nchunks, int np, T* __restrict__ out, long ostride) {
+    const int b = blockIdx.z;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= np) return;
+    T s = T(0);
+    for (int c = j / 256; c < nchunks; c++) s += part[((long)b * nchunks + c) * np + j];
+    out[(long)b * ostride + j] = s;
+}
+
+// Fused LML-gradient contraction over one lower 64x64 tile of K^-1 (never materialises the (n, n, d+1)
+// tensor of src/gpr/matern_kernel.rs:83-135 / product_kernel.rs:40-70):
+//   g_k = 1/2 sum_ij (alpha_i alpha_j - Kinv_ij) G_ijk,   k = noise, c, l_1..l_d   (lml.rs:61-71)
+// gpart[b][tile][0..p) receives this tile's contribution (symmetry: off-diagonal cells count twice).
+template <typename T, int NU2>
+__global__ void __launch_bounds__(256) k_grad_contract(const T* __restrict__ Kinv, long mstride, int n, int d,
+                                                       int np, const T* __restrict__ xsT,
+                                                       const T* __restrict__ alpha, long astride,
+                                                       const T* __restrict__ prm, int pstride,
+                                                       double* __restrict__ gpart, long gp_bstride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* xi = reinterpret_cast<T*>(smem_raw);  // [d][64]
+    T* xj = xi + d * TILE;                   // [d][64]
+    T* ai = xj + d * TILE;                   // [64]
+    T* aj = ai + TILE;                       // [64]
+    double* wsum = reinterpret_cast<double*>(aj + TILE);  // [8][p]
+    const int p = d + 2;
+    int mt, nt;
+    lower_tile(blockIdx.x, mt, nt);
+    const int b = blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i0 = mt * TILE, j0 = nt * TILE;
+    const T* xb = xsT + (long)b * d * np;
+    for (int e = tid; e < d * TILE; e += 256) {
+        int k = e / TILE, r = e % TILE;
+        xi[e] = xb[(long)k * np + i0 + r];
+        xj[e] = xb[(long)k * np + j0 + r];
+    }
+    if (tid < TILE) ai[tid] = alpha[(long)b * astride + i0 + tid];
+    else if (tid < 2 * TILE) aj[tid - TILE] = alpha[(long)b * astride + j0 + tid - TILE];
+    __syncthreads();
+    const T noise = prm[(long)b * pstride + 0], c = prm[(long)b * pstride + 1];
+    const int tx = tid & 15, ty = tid >> 4;
+    const T* Kb = Kinv + (long)b * mstride;
+    T cm[16];
+    double g_noise = 0.0, g_c = 0.0;
+    {
+        T S[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) S[e] = T(0);
+        for (int k = 0; k < d; k++) {
+            T vi[4], vj[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) vi[a] = xi[k * TILE + ty + 16 * a];
+#pragma unroll
+            for (int q = 0; q < 4; q++) vj[q] = xj[k * TILE + tx + 16 * q];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    T df = vi[a] - vj[q];
+                    S[a * 4 + q] += df * df;
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int li = ty + 16 * a, lj = tx + 16 * q;
+                const int gi = i0 + li, gj = j0 + lj;
+                T wgt = T(2);
+                if (mt == nt) wgt = (li > lj) ? T(2) : ((li == lj) ? T(1) : T(0));
+                if (gi >= n || gj >= n) wgt = T(0);
+                const T tij = ai[li] * aj[lj] - Kb[(long)gi * np + gj];
+                const T s = S[a * 4 + q];
+                T base, dk_factor, kval;
+                if (NU2 == 5) {
+                    const T t = dev_sqrt<T>(T(5) * s);
+                    const T e = dev_exp<T>(-t);
+                    kval = (T(1) + t + t * t / T(3)) * e;
+                    dk_factor = e * (t + T(1)) * T(5.0 / 3.0);  // matern_kernel.rs:120-130
+                } else if (NU2 == 3) {
+                    const T t = dev_sqrt<T>(T(3) * s);
+                    const T e = dev_exp<T>(-t);
+                    kval = (t + T(1)) * e;
+                    dk_factor = T(3) * e;  // matern_kernel.rs:112-118
+                } else {
+                    const T r = dev_sqrt<T>(s);
+                    kval = dev_exp<T>(-r);
+                    dk_factor = (r > T(0)) ? kval / r : T(0);  // matern_kernel.rs:102-111 (non-finite -> 0)
+                }
+                base = wgt * tij * c;
+                cm[a * 4 + q] = base * dk_factor;
+                g_c += (double)(base * kval);
+                if (gi == gj) g_noise += (double)(wgt * tij * noise);
+            }
+    }
+    // block-level deterministic reduction: warp shuffle, then warps in order
+    auto warp_sum = [&](double v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
+    g_noise = warp_sum(g_noise);
+    g_c = warp_sum(g_c);
+    if (lane == 0) {
+        wsum[warp * p + 0] = g_noise;
+        wsum[warp * p + 1] = g_c;
+    }
+    for (int k = 0; k < d; k++) {
+        T vi[4], vj[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) vi[a] = xi[k * TILE + ty + 16 * a];
+#pragma unroll
+        for (int q = 0; q < 4; q++) vj[q] = xj[k * TILE + tx + 16 * q];
+        T acc = T(0);
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                T df = vi[a] - vj[q];
+                acc += cm[a * 4 + q] * (df * df);
+            }
+        double v = warp_sum((double)acc);
+        if (lane == 0) wsum[warp * p + 2 + k] = v;
+    }
+    __syncthreads();
+    if (tid < p) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) s += wsum[w * p + tid];
+        gpart[(long)b * gp_bstride + (long)blockIdx.x * p + tid] = 0.5 * s;
+    }
+}
+
+// Finishes one evaluation: lml = -1/2 y.alpha - sum ln L_ii - n/2 ln 2pi (lml.rs:57-59) and the sum of the
+// per-tile gradient partials in tile order.  One CTA per batch element.
+template <typename T>
+__global__ void __launch_bounds__(256) k_finish(const T* __restrict__ y, const T* __restrict__ alpha, long astride,
+                                                int n, int np, const T* __restrict__ ldp, int ldp_stride,
+                                                const double* __restrict__ gpart, long gp_bstride, int ntiles,
+                                                int p, const int* __restrict__ status, double* __restrict__ lml,
+                                                double* __restrict__ grad, int want_grad) {
+    __shared__ double red[256];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const bool bad = status[b] != 0;
+    double s = 0.0;
+    for (int i = tid; i < n; i += 256) s += (double)(y[i] * alpha[(long)b * astride + i]);
+    red[tid] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) red[tid] += red[tid + o];
+        __syncthreads();
+    }
+    const double ya = red[0];
+    __syncthreads();
+    s = 0.0;
+    for (int i = tid; i < np / TILE; i += 256) s += (double)ldp[(long)b * ldp_stride + i];
+    red[tid] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) red[tid] += red[tid + o];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        double v = -0.5 * ya - red[0] - 0.5 * (double)n * 1.8378770664093454836;  // ln(2 pi)
+        if (bad || !(v == v)) v = -INFINITY;
+        lml[b] = v;
+    }
+    if (!want_grad) return;
+    // gradient: p columns; thread groups of (256 / p') walk the tiles with a fixed stride
+    const bool isbad = bad;
+    for (int k = 0; k < p; k++) {
+        __syncthreads();
+        double acc = 0.0;
+        for (int t = tid; t < ntiles; t += 256) acc += gpart[(long)b * gp_bstride + (long)t * p + k];
+        red[tid] = acc;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (tid < o) red[tid] += red[tid + o];
+            __syncthreads();
+        }
+        if (tid == 0) grad[(long)b * p + k] = isbad ? 0.0 : red[0];
+    }
+}
+
+// ------------------------------------------------------------------------------------------- predict
+// Cross-kernel tile rows: for 64 candidates per CTA, k*[r][j] = c * matern(|xs_r / l - xsT_j|) over all
+// train columns, mean[r] = sum_j k*[r][j] alpha[j] (src/gpr/predict.rs:18-19).  k* is written out
+// (leading dimension np, zero in the padding columns) only when kstar != nullptr.
+template <typename T, int NU2>
+__global__ void __launch_bounds__(256) k_kstar_mean(const T* __restrict__ xs, long m, long row0, int d,
+                                                    const T* __restrict__ xsT_train, int n, int np,
+                                                    const T* __restrict__ ls, T c, const T* __restrict__ alpha,
+                                                    T* __restrict__ kstar, T* __restrict__ mean) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* xc = reinterpret_cast<T*>(smem_raw);  // [d][64] candidates (scaled)
+    T* xt = xc + d * TILE;                   // [d][64] train tile
+    T* al = xt + d * TILE;                   // [64]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const long r0 = (long)blockIdx.x * TILE;  // row within the chunk
+    for (int e = tid; e < d * TILE; e += 256) {
+        int r = e / d, k = e % d;  // coalesced read of the row-major candidates
+        long gr = row0 + r0 + r;
+        xc[k * TILE + r] = (gr < m) ? xs[gr * d + k] / ls[k] : T(0);
+    }
+    T macc[4] = {T(0), T(0), T(0), T(0)};
+    for (int j0 = 0; j0 < np; j0 += TILE) {
+        __syncthreads();
+        for (int e = tid; e < d * TILE; e += 256) {
+            int k = e / TILE, r = e % TILE;
+            xt[e] = xsT_train[(long)k * np + j0 + r];
+        }
+        if (tid < TILE) al[tid] = alpha[j0 + tid];
+        __syncthreads();
+        T acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[a][q] = T(0);
+        for (int k = 0; k < d; k++) {
+            T vi[4], vj[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) vi[a] = xc[k * TILE + ty + 16 * a];
+#pragma unroll
+            for (int q = 0; q < 4; q++) vj[q] = xt[k * TILE + tx + 16 * q];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    T df = vi[a] - vj[q];
+                    acc[a][q] += df * df;
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int gj = j0 + tx + 16 * q;
+                T v = (gj < n) ? c * matern_corr<T, NU2>(dev_sqrt<T>(acc[a][q])) : T(0);
+                macc[a] += v * al[tx + 16 * q];
+                if (kstar != nullptr) kstar[(r0 + ty + 16 * a) * (long)np + gj] = v;
+            }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        T v = macc[a];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        long gr = row0 + r0 + ty + 16 * a;
+        if (tx == 0 && gr < m) mean[gr] = v;
+    }
+}
+
+// var[r] = c + 1e-5 - sum_t part[r][t]; counts values < -sqrt(1e-5) then clamps at 0
+// (src/gpr/predict.rs:25-48, :104-127).
+template <typename T>
+__global__ void k_var_finish(const T* __restrict__ part, int ld, int ntiles, long rows, long m, long row0, T c,
+                             T* __restrict__ var, unsigned long long* __restrict__ n_below) {
+    long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows || row0 + r >= m) return;
+    T s = T(0);
+    for (int t = 0; t < ntiles; t++) s += part[r * ld + t];
+    const T min_noise = T(1e-5);
+    T v = c + min_noise - s;
+    if (v < -dev_sqrt<T>(min_noise)) atomicAdd(n_below, 1ULL);
+    if (v < T(0)) v = T(0);
+    var[row0 + r] = v;
+}
+
+// out[i][j] = (i >= j) ? in[i][j] : in[j][i] for i, j < n  (hermitian fill of potri, lml.rs:62), packed n x n
+template <typename T>
+__global__ void k_sym_fill(const T* __restrict__ in, int np, int n, T* __restrict__ out, int mode) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= n || i >= n) return;
+    T v;
+    if (mode == 0) v = (i >= j) ? in[(long)i * np + j] : in[(long)j * np + i];  // symmetric
+    else v = (i >= j) ? in[(long)i * np + j] : T(0);                             // lower only
+    out[(long)i * n + j] = v;
+}
+
+}  // namespace hbegp

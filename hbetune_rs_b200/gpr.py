@@ -1,0 +1,334 @@
+"""Host-side mirror of the reference's ``src/gpr`` surface on top of the C ABI.
+
+Kernel *objects* only carry hyper-parameters and bounds (``BoundedValue``, ``ConstantKernel``,
+``Matern``, ``Product`` — same names and theta conventions as ``src/gpr/*_kernel.rs``); every kernel
+*evaluation* happens on the GPU inside ``libhbegp.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import sys
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+
+
+class BoundsError(ValueError):
+    """``src/util/bounded_value.rs:72-77``."""
+
+    def __init__(self, value, lo, hi):
+        super().__init__(f"value {value} violated bounds [{lo}, {hi}]")
+        self.value, self.min, self.max = value, lo, hi
+
+
+@dataclass(frozen=True)
+class BoundedValue:
+    """``src/util/bounded_value.rs:3-56``."""
+
+    value: float
+    min: float
+    max: float
+
+    def __post_init__(self):
+        if not (self.min <= self.value <= self.max):
+            raise BoundsError(self.value, self.min, self.max)
+
+    def with_value(self, value):
+        return BoundedValue(value, self.min, self.max)
+
+    def with_clamped_value(self, value):
+        if value < self.min:
+            value = self.min
+        elif self.max < value:
+            value = self.max
+        return BoundedValue(value, self.min, self.max)
+
+
+class ConstantKernel:
+    """``src/gpr/constant_kernel.rs:9-67`` (parameters only)."""
+
+    def __init__(self, constant: BoundedValue):
+        self.constant = constant
+
+    def n_params(self):
+        return 1
+
+    def theta(self):
+        return [math.log(self.constant.value)]
+
+    def with_theta(self, theta):
+        (t,) = theta
+        return ConstantKernel(self.constant.with_value(math.exp(t)))
+
+    def with_clamped_theta(self, theta):
+        (t,) = theta
+        return ConstantKernel(self.constant.with_clamped_value(math.exp(t)))
+
+    def bounds(self):
+        return [(math.log(self.constant.min), math.log(self.constant.max))]
+
+    def natural_bounds(self):
+        return [(self.constant.min, self.constant.max)]
+
+
+class Matern:
+    """``src/gpr/matern_kernel.rs:12-187`` (parameters only; nu in {0.5, 1.5, 2.5})."""
+
+    def __init__(self, nu: float, length_scale: Sequence[BoundedValue]):
+        self.nu = nu
+        self.length_scale = list(length_scale)
+
+    def n_params(self):
+        return len(self.length_scale)
+
+    def theta(self):
+        return [math.log(b.value) for b in self.length_scale]
+
+    def with_theta(self, theta):
+        assert len(theta) == self.n_params()
+        return Matern(self.nu, [b.with_value(math.exp(t)) for t, b in zip(theta, self.length_scale)])
+
+    def with_clamped_theta(self, theta):
+        assert len(theta) == self.n_params()
+        return Matern(self.nu, [b.with_clamped_value(math.exp(t)) for t, b in zip(theta, self.length_scale)])
+
+    def bounds(self):
+        return [(math.log(b.min), math.log(b.max)) for b in self.length_scale]
+
+    def natural_bounds(self):
+        return [(b.min, b.max) for b in self.length_scale]
+
+
+class Product:
+    """``src/gpr/product_kernel.rs:8-109`` specialised like the reference's production kernel
+    ``Product<ConstantKernel, Matern>`` (``src/core/gpr.rs:51``)."""
+
+    def __init__(self, k1: ConstantKernel, k2: Matern):
+        self.k1, self.k2 = k1, k2
+
+    def n_params(self):
+        return self.k1.n_params() + self.k2.n_params()
+
+    def theta(self):
+        return self.k1.theta() + self.k2.theta()
+
+    def with_theta(self, theta):
+        assert len(theta) == self.n_params()
+        return Product(self.k1.with_theta(theta[:1]), self.k2.with_theta(theta[1:]))
+
+    def with_clamped_theta(self, theta):
+        assert len(theta) == self.n_params()
+        return Product(self.k1.with_clamped_theta(theta[:1]), self.k2.with_clamped_theta(theta[1:]))
+
+    def bounds(self):
+        return self.k1.bounds() + self.k2.bounds()
+
+    def natural_bounds(self):
+        return self.k1.natural_bounds() + self.k2.natural_bounds()
+
+
+def _np_dtype(dtype: int):
+    return np.float64 if dtype == _lib.F64 else np.float32
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One GPU context (``hbegp_ctx``).  ``stream`` is a raw ``cudaStream_t`` (e.g.
+    ``torch.cuda.current_stream().cuda_stream``) or None."""
+
+    def __init__(self, device: int = 0, dtype: int = _lib.F64, stream: Optional[int] = None):
+        self.dtype = dtype
+        self.A = _np_dtype(dtype)
+        h = C.c_void_p()
+        check(lib.hbegp_ctx_create(device, dtype, C.c_void_p(stream) if stream else None, C.byref(h)), "hbegp_ctx_create")
+        self._h = h
+        self.n = self.d = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.hbegp_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib.hbegp_ctx_launch_count(self._h))
+
+    def set_workspace_limit(self, nbytes: int):
+        check(lib.hbegp_ctx_set_workspace_limit(self._h, nbytes), "hbegp_ctx_set_workspace_limit")
+
+    def set_data(self, x: np.ndarray, y: np.ndarray):
+        x = np.ascontiguousarray(x, dtype=self.A)
+        y = np.ascontiguousarray(y, dtype=self.A)
+        assert x.ndim == 2 and y.shape == (x.shape[0],)
+        check(lib.hbegp_set_data(self._h, x.shape[0], x.shape[1], _ptr(x), _ptr(y)), "hbegp_set_data")
+        self.n, self.d = x.shape
+
+    def set_data_device(self, n: int, d: int, x_ptr: int, y_ptr: int):
+        check(lib.hbegp_set_data_device(self._h, n, d, C.c_void_p(x_ptr), C.c_void_p(y_ptr)), "hbegp_set_data_device")
+        self.n, self.d = n, d
+
+    def lml_grad_batch(self, theta: np.ndarray, nu: float = 2.5, lo=None, hi=None, want_grad: bool = True):
+        theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        B, p = theta.shape
+        assert p == self.d + 2
+        lo = None if lo is None else np.ascontiguousarray(lo, dtype=np.float64)
+        hi = None if hi is None else np.ascontiguousarray(hi, dtype=np.float64)
+        lml = np.empty(B)
+        grad = np.empty((B, p)) if want_grad else None
+        status = np.empty(B, dtype=np.int32)
+        check(lib.hbegp_lml_grad_batch(self._h, nu, B, _ptr(theta), _ptr(lo), _ptr(hi), _ptr(lml), _ptr(grad),
+                                       _ptr(status)), "hbegp_lml_grad_batch")
+        return lml, grad, status
+
+    def fit_runs(self, starts: np.ndarray, lo, hi, nu: float = 2.5, maxeval: int = 150):
+        starts = np.ascontiguousarray(np.atleast_2d(starts), dtype=np.float64)
+        R, p = starts.shape
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        res = (_lib.RunResult * R)()
+        best_theta = np.empty((R, p))
+        check(lib.hbegp_fit_runs(self._h, nu, R, _ptr(starts), _ptr(lo), _ptr(hi), maxeval, res, _ptr(best_theta)),
+              "hbegp_fit_runs")
+        return res, best_theta
+
+    def debug_factor(self, theta, nu: float = 2.5, want=("k", "w", "kinv")):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        out = {k: (np.empty((self.n, self.n), dtype=self.A) if k in want else None) for k in ("k", "w", "kinv")}
+        st = C.c_int(0)
+        check(lib.hbegp_debug_factor(self._h, nu, _ptr(theta), _ptr(out["k"]), _ptr(out["w"]),
+                                     _ptr(out["kinv"]), C.byref(st)), "hbegp_debug_factor")
+        out["status"] = st.value
+        return out
+
+    def model(self, theta, nu: float = 2.5, lo=None, hi=None, want_alpha=True, want_kinv=False) -> "Model":
+        return Model(self, theta, nu, lo, hi, want_alpha, want_kinv)
+
+
+class Model:
+    """A fitted model resident on the GPU (``hbegp_model``): X, alpha and L^-1 stay in HBM."""
+
+    def __init__(self, ctx: Context, theta, nu=2.5, lo=None, hi=None, want_alpha=True, want_kinv=False):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        lo = None if lo is None else np.ascontiguousarray(lo, dtype=np.float64)
+        hi = None if hi is None else np.ascontiguousarray(hi, dtype=np.float64)
+        self.ctx, self.A = ctx, ctx.A
+        self.alpha = np.empty(ctx.n, dtype=self.A) if want_alpha else None
+        self.k_inv = np.empty((ctx.n, ctx.n), dtype=self.A) if want_kinv else None
+        h = C.c_void_p()
+        lml = C.c_double()
+        rc = lib.hbegp_model_create(ctx._h, nu, _ptr(theta), _ptr(lo), _ptr(hi), C.byref(h), C.byref(lml),
+                                    _ptr(self.alpha), _ptr(self.k_inv))
+        if rc == _lib.NOT_PD:
+            raise np.linalg.LinAlgError("Kernel matrix must be invertible.")  # fit.rs:55 panics here
+        check(rc, "hbegp_model_create")
+        self._h = h
+        self.lml = lml.value
+        self.n, self.d = ctx.n, ctx.d
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.hbegp_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def predict(self, xs: np.ndarray, want_variance: bool = True, warn: bool = True):
+        xs = np.ascontiguousarray(xs, dtype=self.A)
+        assert xs.ndim == 2 and xs.shape[1] == self.d
+        m = xs.shape[0]
+        mean = np.empty(m, dtype=self.A)
+        var = np.empty(m, dtype=self.A) if want_variance else None
+        nb = C.c_long(0)
+        check(lib.hbegp_predict(self._h, m, _ptr(xs), _ptr(mean), _ptr(var), C.byref(nb)), "hbegp_predict")
+        if warn and nb.value:
+            # predict.rs:39-46 prints the offending values; the device path reports their count
+            print(f"Variances below 0 were predicted and will be corrected: {nb.value} value(s)", file=sys.stderr)
+        self.n_below_warn = nb.value
+        return mean, var
+
+    def predict_device(self, m: int, xs_ptr: int, mean_ptr: int, var_ptr: Optional[int] = None):
+        check(lib.hbegp_predict_device(self._h, m, C.c_void_p(xs_ptr), C.c_void_p(mean_ptr),
+                                       C.c_void_p(var_ptr) if var_ptr else None, None), "hbegp_predict_device")
+
+
+@dataclass
+class FittedKernel:
+    """``src/gpr/fit.rs:6-12``; ``model`` is the device-resident counterpart of (alpha, k_inv)."""
+
+    kernel: Product
+    noise: BoundedValue
+    alpha: np.ndarray
+    k_inv: Optional[np.ndarray]
+    lml: float
+    model: Model
+    n_evals: int = 0
+
+    @staticmethod
+    def _theta_bounds(kernel: Product, noise: BoundedValue):
+        lo = np.array([noise.min] + [b[0] for b in kernel.natural_bounds()])
+        hi = np.array([noise.max] + [b[1] for b in kernel.natural_bounds()])
+        return lo, hi
+
+    @classmethod
+    def new(cls, ctx: Context, kernel: Product, x_train, y_train, rng, n_restarts_optimizer: int,
+            noise: BoundedValue, maxeval: int = 150, want_kinv: bool = False, shard=None) -> "FittedKernel":
+        """``FittedKernel::new`` (``src/gpr/fit.rs:18-31, 71-176``).  ``rng`` needs ``uniform_inclusive``;
+        start points are drawn in reference order (``gradmin.rs:21-24``) before any optimisation runs.
+        ``shard`` (optional) is a callable ``(starts, run_fn) -> (results, thetas)`` distributing runs."""
+        ctx.set_data(x_train, y_train)
+        lo, hi = cls._theta_bounds(kernel, noise)
+        tb = [(math.log(a), math.log(b)) for a, b in zip(lo, hi)]
+        theta0 = [math.log(noise.value)] + kernel.theta()
+        starts = [theta0] + [[rng.uniform_inclusive(a, b) for a, b in tb] for _ in range(n_restarts_optimizer)]
+        starts = np.array(starts, dtype=np.float64)
+        nu = kernel.k2.nu
+        if shard is None:
+            res, thetas = ctx.fit_runs(starts, lo, hi, nu, maxeval)
+        else:
+            res, thetas = shard(starts, lambda s: ctx.fit_runs(s, lo, hi, nu, maxeval))
+        best = lib.hbegp_pick_best_run(len(res), res)
+        if best < 0:
+            raise RuntimeError("called `Option::unwrap()` on a `None` value")  # fit.rs:161
+        theta = thetas[best]
+        k = kernel.with_clamped_theta(list(theta[1:]))
+        nz = noise.with_clamped_value(float(ctx.A(math.exp(theta[0]))))
+        model = ctx.model(theta, nu, lo, hi, want_alpha=True, want_kinv=want_kinv)
+        return cls(k, nz, model.alpha, model.k_inv, res[best].best_lml, model, sum(r.n_evals for r in res))
+
+    @classmethod
+    def extend(cls, ctx: Context, kernel: Product, x_train, y_train, noise: BoundedValue,
+               want_kinv: bool = False) -> "FittedKernel":
+        """``FittedKernel::extend`` (``src/gpr/fit.rs:33-68``): one evaluation, no optimisation."""
+        ctx.set_data(x_train, y_train)
+        theta = np.array([math.log(noise.value)] + kernel.theta())
+        try:
+            model = ctx.model(theta, kernel.k2.nu, None, None, want_alpha=True, want_kinv=want_kinv)
+        except np.linalg.LinAlgError:
+            raise RuntimeError("Kernel matrix must be invertible.")
+        return cls(kernel, noise, model.alpha, model.k_inv, model.lml, model, 1)
+
+
+def predict(fitted: FittedKernel, x, want_variance: Optional[np.ndarray] = None):
+    """``src/gpr/predict.rs:7-52``: returns the mean; fills ``want_variance`` in place when given."""
+    mean, var = fitted.model.predict(x, want_variance is not None)
+    if want_variance is not None:
+        want_variance[...] = var
+    return mean

@@ -1,0 +1,140 @@
+/*
+ * hbegp.h — C ABI of libhbegp.so: the B200-native Gaussian-process surrogate hot path of hbetune.
+ *
+ * The reference (latk/hbetune.rs) has no FFI or plugin ABI; its seam is a pair of Rust traits
+ * (src/core/surrogate_model.rs:6-65).  This header is the boundary a Rust `impl Estimator<A>` /
+ * `impl SurrogateModel<A>` binds to (INTEGRATION.md shows the `extern "C"` block).  Each entry
+ * point names the reference code it replaces.
+ *
+ * Conventions
+ *  - All pointers are HOST pointers unless the name ends in `_device`; arrays are row-major and
+ *    caller-owned.  `void*` data arrays hold f64 (HBEGP_F64) or f32 (HBEGP_F32, `--use-32`,
+ *    src/bin/hbetune/main.rs:240-244) elements; hyper-parameters are always f64
+ *    (src/gpr/matern_kernel.rs:12-15).
+ *  - theta layout everywhere: [ln noise, ln c, ln l_1 .. ln l_d], p = d + 2 (src/gpr/fit.rs:140-144).
+ *  - Every function returns an int status: 0 ok, < 0 error (never aborts the process).  Per-evaluation
+ *    "kernel matrix not positive definite" (src/gpr/lml.rs:47-50) is reported in a status array as
+ *    HBEGP_NOT_PD, not as an error.
+ *  - A context is bound to one GPU and is used from one thread at a time (the reference's model calls
+ *    all happen on the minimizer's thread, src/gpr/fit.rs:92 uses a RefCell).
+ *  - There is no CPU fallback: without a CUDA device every compute entry point fails with HBEGP_ERR_CUDA.
+ */
+#ifndef HBEGP_H
+#define HBEGP_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HBEGP_F64 0
+#define HBEGP_F32 1
+
+#define HBEGP_OK 0
+#define HBEGP_NOT_PD 1            /* per-evaluation status: Cholesky failed (lml.rs:47-50) */
+#define HBEGP_ERR_INVALID (-1)    /* bad argument / call order */
+#define HBEGP_ERR_CUDA (-2)       /* CUDA runtime failure (incl. no device) */
+#define HBEGP_ERR_NOMEM (-3)      /* device memory exhausted */
+#define HBEGP_ERR_UNSUPPORTED (-4)/* e.g. Matern nu other than 0.5 / 1.5 / 2.5 */
+#define HBEGP_ERR_NO_CAPTURE (-5) /* fit: no evaluation succeeded (fit.rs:161 unwrap panic) */
+
+typedef struct hbegp_ctx hbegp_ctx;
+typedef struct hbegp_model hbegp_model;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+const char* hbegp_version(void);
+/* Last error message of this thread (valid until the next failing call on the thread). */
+const char* hbegp_last_error(void);
+
+/* ---- context ---------------------------------------------------------------------------------- */
+/* `stream` is a cudaStream_t (NULL: the library creates its own); all work of the context is ordered
+ * after / before work on that stream, so CUDA events recorded on it bracket the library's kernels. */
+int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out);
+int hbegp_ctx_destroy(hbegp_ctx* ctx);
+/* Caps the device memory the context may use for batched evaluation workspaces (0: default 70% of free). */
+int hbegp_ctx_set_workspace_limit(hbegp_ctx* ctx, unsigned long long bytes);
+/* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
+long long hbegp_ctx_launch_count(hbegp_ctx* ctx);
+
+/* Training data of the current fit: X (n x d), y (n).  Replaces the x_train / y_train arguments of
+ * LmlWithGradient::of (src/gpr/lml.rs:16-27) and FittedKernel::new (src/gpr/fit.rs:18-31). */
+int hbegp_set_data(hbegp_ctx* ctx, long n, int d, const void* x, const void* y);
+int hbegp_set_data_device(hbegp_ctx* ctx, long n, int d, const void* x_device, const void* y_device);
+
+/* ---- LML + gradient, batched over thetas ------------------------------------------------------- */
+/* B evaluations of src/gpr/lml.rs:29-79 for Product<ConstantKernel, Matern(nu)> + noise, one per theta
+ * row.  `lo`/`hi` (natural units, length p, may be NULL) clamp exp(theta[1..]) like with_clamped_theta
+ * (src/gpr/fit.rs:95; noise is not clamped).  Outputs: lml[B]; grad[B*p] (may be NULL: value only);
+ * status[B] in {HBEGP_OK, HBEGP_NOT_PD}; on NOT_PD lml = -inf and grad = 0 (fit.rs:103-113 returns +inf
+ * for -lml with a zero gradient). */
+int hbegp_lml_grad_batch(hbegp_ctx* ctx, double nu, int B, const double* theta, const double* lo,
+                         const double* hi, double* lml, double* grad, int* status);
+
+/* ---- restart loop ------------------------------------------------------------------------------ */
+typedef struct hbegp_run_result {
+    double best_lml;      /* largest LML seen at ANY evaluation of this run (fit.rs:115-125)        */
+    long long best_eval;  /* index (0-based, within the run) of the first evaluation that reached it */
+    long long n_evals;    /* evaluations this run performed (<= maxeval)                            */
+    double final_f;       /* optimiser's final objective value (= -lml), gradmin.rs:56-59           */
+    int status;           /* HBEGP_OK, or HBEGP_NOT_PD if no evaluation of the run succeeded        */
+    int reserved;
+} hbegp_run_result;
+
+/* Runs `n_runs` independent bounded L-BFGS optimisations of -LML (src/util/gradmin.rs:35-60: box bounds,
+ * maxeval evaluations) from the given start points, all runs advancing in lockstep so that each
+ * optimiser step is ONE batched GPU evaluation.  This is the shardable unit of the restart loop
+ * (src/util/gradmin.rs:19-30): rank r of G passes the runs it owns.  bounds_lo/bounds_hi: natural
+ * units, length p (theta bounds are their logs, fit.rs:140 / kernel.bounds()).
+ * Outputs per run: results[n_runs], best_theta[n_runs*p] (the theta of the best evaluation). */
+int hbegp_fit_runs(hbegp_ctx* ctx, double nu, int n_runs, const double* starts, const double* bounds_lo,
+                   const double* bounds_hi, int maxeval, hbegp_run_result* results, double* best_theta);
+
+/* Deterministic winner pick over runs in reference order (fit.rs:116-117: strict `>`, so the earliest
+ * (run, evaluation) wins ties).  Returns the winning run index or -1 if none succeeded. */
+int hbegp_pick_best_run(int n_runs, const hbegp_run_result* results);
+
+/* ---- fitted model ------------------------------------------------------------------------------ */
+/* One evaluation at `theta` and the prediction pre-computations of src/gpr/fit.rs:155-175 (also the whole
+ * of FittedKernel::extend, fit.rs:33-68).  The model keeps X, alpha and the inverse Cholesky factor on
+ * the device.  Optional host outputs: lml, alpha_out[n], kinv_out[n*n] (full symmetric K^-1, the
+ * reference's `k_inv`).  Returns HBEGP_NOT_PD (and no model) if the kernel matrix is not invertible
+ * (the reference panics there, fit.rs:55). */
+int hbegp_model_create(hbegp_ctx* ctx, double nu, const double* theta, const double* lo, const double* hi,
+                       hbegp_model** out, double* lml, void* alpha_out, void* kinv_out);
+int hbegp_model_destroy(hbegp_model* model);
+long hbegp_model_n(const hbegp_model* model);
+int hbegp_model_dim(const hbegp_model* model);
+
+/* src/gpr/predict.rs:7-52: mean[m] = k* alpha; if var != NULL: var[m] = c + 1e-5 - k* K^-1 k*^T, values
+ * below 0 clamped to 0; *n_below_warn (may be NULL) counts values < -sqrt(1e-5) BEFORE clamping, i.e. the
+ * entries the reference lists in its stderr warning (predict.rs:39-46). */
+int hbegp_predict(hbegp_model* model, long m, const void* xs, void* mean, void* var, long* n_below_warn);
+/* Same with device-resident candidates and outputs (asynchronous on the context's stream). */
+int hbegp_predict_device(hbegp_model* model, long m, const void* xs_device, void* mean_device,
+                         void* var_device, long* n_below_warn_device);
+
+/* ---- host-side pieces of the reference interface (no GPU needed) -------------------------------- */
+/* Bounded L-BFGS used by hbegp_fit_runs, exposed with a callback objective
+ * (objective(x, grad_out, user) -> f), mirroring minimize_by_gradient (src/util/gradmin.rs:35-60).
+ * x[n] is updated in place; returns the number of evaluations (>= 0) or an error. */
+typedef double (*hbegp_objective_fn)(const double* x, double* grad_out, void* user);
+int hbegp_minimize_by_gradient(hbegp_objective_fn objective, void* user, int n, double* x,
+                               const double* lo, const double* hi, int maxeval, double* f_out);
+
+/* Xoshiro256** restart-start sampler: src/core/random.rs + src/util/gradmin.rs:21-24.  `state[4]` is the
+ * generator state (updated).  hbegp_rng_seed = RNG::new_with_seed, hbegp_rng_fork = fork_random_state,
+ * hbegp_rng_uniform = rng.uniform(lo..=hi). */
+void hbegp_rng_seed(unsigned long long seed, unsigned long long state[4]);
+void hbegp_rng_fork(unsigned long long state[4], unsigned long long child[4]);
+double hbegp_rng_uniform(unsigned long long state[4], double lo, double hi);
+
+/* ---- debugging / parity aids -------------------------------------------------------------------- */
+/* Copies out intermediates of ONE evaluation at theta (any pointer may be NULL): k[n*n] lower triangle of
+ * K + noise I (upper = 0), w[n*n] = L^-1 (the inverse Cholesky factor; L itself is consumed by the fused
+ * factor-and-invert recursion), kinv[n*n] full symmetric. */
+int hbegp_debug_factor(hbegp_ctx* ctx, double nu, const double* theta, void* k, void* w, void* kinv,
+                       int* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HBEGP_H */

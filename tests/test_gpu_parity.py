@@ -1,0 +1,174 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Tolerances: f64 relative 1e-9, f32 relative 1e-4 (BASELINE.json north_star), with the
+conditioning caveat of SURVEY.md H3: variances are compared as |d var| <= tol * (c + 1e-5), and the
+synthetic thetas keep noise >= 1e-2."""
+import math
+
+import numpy as np
+import pytest
+
+from tests.util import oracle_kernel, oracle_lml, random_thetas, synth
+from oracle import gpr as ogpr
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float64: 1e-9, np.float32: 1e-4}
+
+
+def _ctx(A):
+    import hbetune_rs_b200 as h
+    return h.Context(0, h.F64 if A == np.float64 else h.F32)
+
+
+@pytest.mark.parametrize("n,d", [(1, 1), (3, 2), (64, 2), (65, 3), (100, 3), (200, 5), (333, 8)])
+def test_factor_intermediates_f64(n, d):
+    A = np.float64
+    x, y = synth(n, d)
+    theta = random_thetas(1, d, seed=n)[0]
+    with _ctx(A) as ctx:
+        ctx.set_data(x, y)
+        out = ctx.debug_factor(theta)
+    assert out["status"] == 0
+    kern = oracle_kernel(theta)
+    k_ref = kern.kernel(x, x, A) + math.exp(theta[0]) * np.eye(n)
+    np.testing.assert_allclose(out["k"], np.tril(k_ref), rtol=1e-12, atol=1e-14)
+    l_ref = np.linalg.cholesky(k_ref)
+    w_ref = np.linalg.inv(l_ref)
+    np.testing.assert_allclose(out["w"], w_ref, rtol=0, atol=1e-9 * np.abs(w_ref).max())
+    kinv_ref = ogpr.factorizec(k_ref.copy(), A).invc()
+    np.testing.assert_allclose(out["kinv"], kinv_ref, rtol=0, atol=1e-9 * np.abs(kinv_ref).max())
+
+
+@pytest.mark.parametrize("A", [np.float64, np.float32])
+@pytest.mark.parametrize("n,d,B", [(50, 2, 3), (150, 4, 5), (300, 8, 4)])
+def test_lml_and_gradient_batch(A, n, d, B):
+    x, y = synth(n, d, A=A)
+    thetas = random_thetas(B, d, seed=7 + n, noise=(1e-2, 1.0) if A == np.float64 else (1e-1, 1.0))
+    with _ctx(A) as ctx:
+        ctx.set_data(x, y)
+        lml, grad, status = ctx.lml_grad_batch(thetas)
+        lml_only, none, _ = ctx.lml_grad_batch(thetas, want_grad=False)
+    assert none is None
+    np.testing.assert_array_equal(lml, lml_only)
+    tol = TOL[A]
+    for b in range(B):
+        ref = oracle_lml(thetas[b], x, y, A=A)
+        assert status[b] == 0 and ref is not None
+        assert abs(lml[b] - ref.lml) <= tol * abs(ref.lml), (b, lml[b], ref.lml)
+        g_ref = np.array(ref.lml_gradient)
+        scale = np.abs(g_ref).max()
+        np.testing.assert_allclose(grad[b], g_ref, rtol=tol, atol=tol * scale)
+
+
+@pytest.mark.parametrize("nu", [0.5, 1.5, 2.5])
+def test_matern_nu_variants(nu):
+    A = np.float64
+    x, y = synth(90, 3)
+    thetas = random_thetas(3, 3, seed=11)
+    with _ctx(A) as ctx:
+        ctx.set_data(x, y)
+        lml, grad, status = ctx.lml_grad_batch(thetas, nu=nu)
+    for b in range(3):
+        ref = oracle_lml(thetas[b], x, y, nu=nu)
+        assert abs(lml[b] - ref.lml) <= 1e-9 * abs(ref.lml)
+        g_ref = np.array(ref.lml_gradient)
+        np.testing.assert_allclose(grad[b], g_ref, rtol=1e-8, atol=1e-9 * np.abs(g_ref).max())
+
+
+def test_unsupported_nu_and_errors():
+    import hbetune_rs_b200 as h
+    x, y = synth(10, 2)
+    with _ctx(np.float64) as ctx:
+        with pytest.raises(h.HbegpError) as e:
+            ctx.lml_grad_batch(random_thetas(1, 0))  # no data yet
+        ctx.set_data(x, y)
+        with pytest.raises(h.HbegpError) as e:
+            ctx.lml_grad_batch(random_thetas(1, 2), nu=3.5)
+        assert e.value.code == -4
+
+
+def test_not_positive_definite_is_a_status_not_an_error():
+    A = np.float64
+    x, y = synth(20, 2)
+    x[1] = x[0]  # duplicate row, zero noise, c = 1: the second pivot is exactly 0
+    theta_bad = np.array([-800.0, 0.0, 0.0, 0.0])
+    theta_ok = np.array([math.log(0.1), 0.0, 0.0, 0.0])
+    assert oracle_lml(theta_bad, x, y) is None  # lml.rs:47-50
+    with _ctx(A) as ctx:
+        ctx.set_data(x, y)
+        lml, grad, status = ctx.lml_grad_batch(np.stack([theta_ok, theta_bad, theta_ok]))
+    assert list(status) == [0, 1, 0]
+    assert lml[1] == -math.inf and (grad[1] == 0).all()  # fit.rs:103-113
+    assert np.isfinite(lml[0]) and lml[0] == lml[2]
+
+
+def test_theta_clamping_matches_with_clamped_theta():
+    A = np.float64
+    x, y = synth(40, 2)
+    lo = np.array([1e-5, 0.5, 0.1, 0.1])
+    hi = np.array([1e5, 2.0, 1.0, 1.0])
+    theta = np.array([math.log(0.1), math.log(5.0), math.log(0.01), math.log(0.5)])  # c, l_1 out of bounds
+    clamped = np.array([math.log(0.1), math.log(2.0), math.log(0.1), math.log(0.5)])
+    with _ctx(A) as ctx:
+        ctx.set_data(x, y)
+        a, ga, _ = ctx.lml_grad_batch(theta[None], lo=lo, hi=hi)
+        b, gb, _ = ctx.lml_grad_batch(clamped[None])
+    assert abs(a[0] - b[0]) <= 1e-12 * abs(b[0])
+    np.testing.assert_allclose(ga, gb, rtol=1e-10)
+
+
+@pytest.mark.parametrize("A", [np.float64, np.float32])
+@pytest.mark.parametrize("n,d,m", [(5, 1, 1), (120, 3, 300), (257, 6, 1000), (64, 2, 64)])
+def test_predict_mean_and_variance(A, n, d, m):
+    x, y = synth(n, d, A=A)
+    xs = np.random.default_rng(2).random((m, d)).astype(A)
+    theta = random_thetas(1, d, seed=5, noise=(3e-2, 0.3) if A == np.float64 else (0.1, 0.5))[0]
+    ref = oracle_lml(theta, x, y, A=A)
+    kern = oracle_kernel(theta)
+    kinv_ref = ref.factorization.invc()
+    var_ref = np.zeros(m, dtype=A)
+    mean_ref = ogpr.predict(kern, ref.alpha, xs, x, kinv_ref, var_ref, A)
+    with _ctx(A) as ctx:
+        ctx.set_data(x, y)
+        model = ctx.model(theta, want_kinv=True)
+        mean, var = model.predict(xs)
+        mean_only, none = model.predict(xs, want_variance=False)
+    tol = TOL[A]
+    c = math.exp(theta[1])
+    assert abs(model.lml - ref.lml) <= tol * abs(ref.lml)
+    np.testing.assert_allclose(model.alpha, ref.alpha, rtol=0, atol=tol * 10 * np.abs(ref.alpha).max())
+    np.testing.assert_allclose(model.k_inv, kinv_ref, rtol=0, atol=tol * 10 * np.abs(kinv_ref).max())
+    np.testing.assert_allclose(mean, mean_ref, rtol=0, atol=tol * max(1.0, np.abs(mean_ref).max()))
+    np.testing.assert_allclose(var, var_ref, rtol=0, atol=tol * (c + 1e-5))
+    np.testing.assert_array_equal(mean, mean_only)
+    assert none is None and (var >= 0).all()
+
+
+def test_predict_empty_and_training_points():
+    A = np.float64
+    x, y = synth(80, 2)
+    theta = np.array([math.log(1e-2), 0.0, math.log(0.5), math.log(0.5)])
+    with _ctx(A) as ctx:
+        ctx.set_data(x, y)
+        model = ctx.model(theta)
+        mean, var = model.predict(np.zeros((0, 2)))
+        assert mean.shape == (0,) and var.shape == (0,)
+        mean, var = model.predict(x)
+    # at the training points the posterior variance is below the noise level and non-negative
+    assert (var >= 0).all() and (var < 2e-2).all()
+    assert np.abs(mean - y).max() < 0.5
+
+
+def test_inverse_round_trip_n1024():
+    """Size-independent properties at a BASELINE size (C3: n = 1024, d = 8): W K W^T = I, K^-1 = W^T W, K K^-1 = I."""
+    A = np.float64
+    n, d = 1024, 8
+    x, y = synth(n, d)
+    theta = np.array([math.log(0.05), 0.0] + [math.log(0.7)] * d)
+    with _ctx(A) as ctx:
+        ctx.set_data(x, y)
+        out = ctx.debug_factor(theta)
+    k = out["k"] + np.tril(out["k"], -1).T
+    assert np.abs(out["w"] @ k @ out["w"].T - np.eye(n)).max() < 1e-10  # W = L^-1  <=>  W K W^T = I
+    assert np.abs(out["w"].T @ out["w"] - out["kinv"]).max() < 1e-10 * np.abs(out["kinv"]).max()
+    assert np.abs(out["kinv"] @ k - np.eye(n)).max() < 1e-9
