@@ -53,6 +53,8 @@ PROTOTYPES = {
     "hbegp_rng_seed": (None, [C.c_ulonglong, C.POINTER(C.c_ulonglong)]),
     "hbegp_rng_fork": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "hbegp_rng_uniform": (C.c_double, [C.POINTER(C.c_ulonglong), C.c_double, C.c_double]),
+    "hbegp_bench_phase": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                    C.POINTER(C.c_float)]),
     "hbegp_debug_factor": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(C.c_int)]),
 }

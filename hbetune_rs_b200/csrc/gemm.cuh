@@ -280,12 +280,8 @@ template <typename T, int BM, int BN, int WM, int WN, bool AK, bool BK_>
 inline cudaError_t launch_gemm_cfg(const GemmArgs<T>& a, int batch, cudaStream_t stream) {
     using Cfg = GemmCfg<T, BM, BN, WM, WN, AK, BK_>;
     auto kern = gemm_kernel<T, BM, BN, WM, WN, AK, BK_>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is set once per context (configure_gemms), never here:
+    // this function also runs inside stream captures.
     long tm = a.M / BM, tn = a.N / BN;
     long tiles = a.lower_only ? tm * (tm + 1) / 2 : tm * tn;
     if (tiles <= 0 || batch <= 0) return cudaSuccess;

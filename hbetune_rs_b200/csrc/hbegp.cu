@@ -14,7 +14,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/hbegp.h"
@@ -83,6 +85,7 @@ struct EngineBase {
     virtual int model_create(double nu, const double* theta, const double* lo, const double* hi, Model** out,
                              double* lml, void* alpha_out, void* kinv_out) = 0;
     virtual int debug_factor(double nu, const double* theta, void* k, void* w, void* kinv, int* status) = 0;
+    virtual int bench_phase(double nu, int B, const double* theta, int phase, int reps, float* ms_out) = 0;
 };
 
 struct Model {
@@ -123,12 +126,29 @@ struct Engine : EngineBase {
     // batched workspaces (capacity `cap` evaluations)
     int cap = 0;
     DevBuf A, W, xsT, prm, u, alpha, ldp, tpart, gpart, d_lml, d_grad, d_status;
+    // CUDA graphs of whole batched evaluations, keyed by (nu2, count, want_grad, want_kinv, phase): the fit
+    // loop replays the same launch sequence hundreds of times, and at small n the host launch rate (hundreds
+    // of kernels per evaluation) would otherwise be the bottleneck.
+    struct CachedGraph {
+        cudaGraphExec_t exec = nullptr;
+        long long kernels = 0;
+    };
+    std::map<std::tuple<int, int, int, int, int>, CachedGraph> graphs;
+    bool use_graphs = true;
+    bool streams_forced = false;
     T* h_prm = nullptr;  // pinned staging
     double* h_out = nullptr;
     int* h_status = nullptr;
     size_t h_prm_bytes = 0, h_out_bytes = 0, h_status_bytes = 0;
 
+    void drop_graphs() {
+        for (auto& kv : graphs)
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        graphs.clear();
+    }
+
     ~Engine() override {
+        drop_graphs();
         for (DevBuf* b : {&dX, &dY, &A, &W, &xsT, &prm, &u, &alpha, &ldp, &tpart, &gpart, &d_lml, &d_grad, &d_status})
             b->release();
         if (h_prm) cudaFreeHost(h_prm);
@@ -145,18 +165,23 @@ struct Engine : EngineBase {
         if (n_ <= 0 || d_ <= 0 || !x || !y) return fail(HBEGP_ERR_INVALID, "set_data: n, d must be positive and x, y non-null");
         if (n_ > 46000) return fail(HBEGP_ERR_INVALID, "set_data: n too large for a single-GPU factorisation");
         CUDA_TRY(cudaSetDevice(device));
+        const void *oldx = dX.p, *oldy = dY.p;
+        const bool same_shape = (n == n_ && d == d_);
         n = n_;
         d = d_;
         np = round_up(n, TILE);
         int rc;
         if ((rc = dX.ensure((size_t)n * d * sizeof(T)))) return rc;
         if ((rc = dY.ensure((size_t)np * sizeof(T)))) return rc;
+        if (!same_shape || oldx != dX.p || oldy != dY.p) {
+            drop_graphs();
+            cap = 0;  // workspaces are re-sized lazily
+        }
         cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
         CUDA_TRY(cudaMemsetAsync(dY.p, 0, (size_t)np * sizeof(T), stream));
         CUDA_TRY(cudaMemcpyAsync(dX.p, x, (size_t)n * d * sizeof(T), kind, stream));
         CUDA_TRY(cudaMemcpyAsync(dY.p, y, (size_t)n * sizeof(T), kind, stream));
         if (!on_device) CUDA_TRY(cudaStreamSynchronize(stream));  // the caller may free x / y
-        cap = 0;  // workspaces are re-sized lazily
         return HBEGP_OK;
     }
 
@@ -184,6 +209,7 @@ struct Engine : EngineBase {
         if (fit < 1) return fail(HBEGP_ERR_NOMEM, "workspace limit too small for one n x n evaluation");
         int newcap = std::min(want, fit);
         if (newcap <= cap) return HBEGP_OK;
+        drop_graphs();  // buffers may move
         int rc;
         size_t c = (size_t)newcap;
         if ((rc = A.ensure(c * np * np * sizeof(T)))) return rc;
@@ -287,6 +313,10 @@ struct Engine : EngineBase {
         return HBEGP_OK;
     }
 
+    // `phase` truncates the pipeline for the benchmark's per-phase timings (hbegp_bench_phase):
+    // 0 = assembly only, 1 = + factor/inverse recursion, 2 = + alpha and K^-1, 3 (default) = everything.
+    int phase = 3;
+
     template <int NU2>
     int pipeline_nu(cudaStream_t st, int s0, int cnt, bool want_grad, bool want_kinv) {
         T* Ab = (T*)A.p + (size_t)s0 * mstride();
@@ -303,8 +333,10 @@ struct Engine : EngineBase {
         k_assemble<T, NU2><<<dim3(ntiles_lower(), 1, cnt), 256, xsm, st>>>(xs, (int)n, d, np, pr, p(), Ab, mstride());
         launches++;
         CUDA_TRY(cudaGetLastError());
+        if (phase < 1) return HBEGP_OK;
         int rc;
         if ((rc = chol_inv(st, s0, cnt, 0, np))) return rc;
+        if (phase < 2) return HBEGP_OK;
         // alpha = W^T (W y)   (lml.rs:54 solves K alpha = y through the factorisation)
         k_trmv_lower<T><<<dim3(np / 8, 1, cnt), 256, 0, st>>>(Wb, mstride(), np, (const T*)dY.p, 0, ub, np);
         launches++;
@@ -315,6 +347,7 @@ struct Engine : EngineBase {
         if (want_grad || want_kinv) {
             if ((rc = lauum(st, Ab, Wb, cnt))) return rc;
         }
+        if (phase < 3) return HBEGP_OK;
         if (want_grad) {
             const size_t gsm = xsm + 2 * TILE * sizeof(T) + 8 * (size_t)p() * sizeof(double);
             k_grad_contract<T, NU2><<<dim3(ntiles_lower(), 1, cnt), 256, gsm, st>>>(
@@ -335,12 +368,22 @@ struct Engine : EngineBase {
         return pipeline_nu<1>(st, s0, cnt, want_grad, want_kinv);
     }
 
-    // Evaluates `cnt` <= cap parameter sets already staged in h_prm; results land in h_out / h_status.
-    int run_chunk(int nu2, int cnt, bool want_grad, bool want_kinv) {
+    int n_groups(int cnt) const {
+        int g = (int)sub.size();
+        if (!streams_forced) {
+            // small matrices are latency bound: keep the batch in one launch sequence; large ones fill the
+            // GPU per launch, extra streams only hide the 64x64 leaves behind another group's GEMMs
+            if (np <= 1024) g = 1;
+            else if (np <= 2048) g = 2;
+        }
+        return std::max(1, std::min(g, cnt));
+    }
+
+    // The launch sequence of one batched evaluation (captured into a CUDA graph or issued directly).
+    int issue_chunk(int nu2, int cnt, bool want_grad, bool want_kinv) {
         CUDA_TRY(cudaMemcpyAsync(prm.p, h_prm, (size_t)cnt * p() * sizeof(T), cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemsetAsync(d_status.p, 0, (size_t)cnt * sizeof(int), stream));
-        int groups = std::min<int>((int)sub.size(), cnt);
-        // large matrices fill the GPU on their own: keep the batch together so the GEMM grids stay big
+        const int groups = n_groups(cnt);
         if (groups <= 1) {
             int rc = pipeline(nu2, stream, 0, cnt, want_grad, want_kinv);
             if (rc) return rc;
@@ -361,6 +404,43 @@ struct Engine : EngineBase {
         if (want_grad)
             CUDA_TRY(cudaMemcpyAsync(h_out + cap, d_grad.p, (size_t)cnt * p() * sizeof(double), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaMemcpyAsync(h_status, d_status.p, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        return HBEGP_OK;
+    }
+
+    // Evaluates `cnt` <= cap parameter sets already staged in h_prm; results land in h_out / h_status.
+    int run_chunk(int nu2, int cnt, bool want_grad, bool want_kinv) {
+        const bool legacy = (stream == nullptr || stream == cudaStreamLegacy);
+        if (!use_graphs || legacy) {
+            int rc = issue_chunk(nu2, cnt, want_grad, want_kinv);
+            if (rc) return rc;
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            return HBEGP_OK;
+        }
+        auto key = std::make_tuple(nu2, cnt, (int)want_grad, (int)want_kinv, phase);
+        auto it = graphs.find(key);
+        if (it == graphs.end()) {
+            const long long before = launches;
+            CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
+            int rc = issue_chunk(nu2, cnt, want_grad, want_kinv);
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+            const long long kernels = launches - before;
+            launches = before;
+            if (rc) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc;
+            }
+            if (ce != cudaSuccess) return fail(HBEGP_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+            CachedGraph cg;
+            ce = cudaGraphInstantiate(&cg.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return fail(HBEGP_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+            cg.kernels = kernels;
+            if (graphs.size() > 256) drop_graphs();
+            it = graphs.emplace(key, cg).first;
+        }
+        CUDA_TRY(cudaGraphLaunch(it->second.exec, stream));
+        launches += it->second.kernels;
         CUDA_TRY(cudaStreamSynchronize(stream));
         return HBEGP_OK;
     }
@@ -390,6 +470,37 @@ struct Engine : EngineBase {
 
     int model_create(double nu, const double* theta, const double* lo, const double* hi, Model** out, double* lml,
                      void* alpha_out, void* kinv_out) override;
+
+    int bench_phase(double nu, int B, const double* theta, int ph, int reps, float* ms_out) override {
+        int nu2, rc;
+        if ((rc = nu_to_nu2(nu, &nu2))) return rc;
+        if (B <= 0 || !theta || reps <= 0 || !ms_out) return fail(HBEGP_ERR_INVALID, "bench_phase: bad arguments");
+        CUDA_TRY(cudaSetDevice(device));
+        if ((rc = ensure_capacity(B))) return rc;
+        if (B > cap) return fail(HBEGP_ERR_NOMEM, "bench_phase: batch does not fit the workspace");
+        for (int b = 0; b < B; b++) fill_params(theta + (size_t)b * p(), nullptr, nullptr, h_prm + (size_t)b * p());
+        cudaEvent_t e0, e1;
+        CUDA_TRY(cudaEventCreate(&e0));
+        CUDA_TRY(cudaEventCreate(&e1));
+        phase = ph;
+        rc = run_chunk(nu2, B, true, false);  // warm-up
+        float total = 0.f;
+        for (int r = 0; r < reps && rc == HBEGP_OK; r++) {
+            cudaEventRecord(e0, stream);
+            rc = run_chunk(nu2, B, true, false);
+            cudaEventRecord(e1, stream);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            total += ms;
+        }
+        phase = 3;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        if (rc) return rc;
+        *ms_out = total / reps;
+        return HBEGP_OK;
+    }
 
     int debug_factor(double nu, const double* theta, void* k, void* w, void* kinv, int* status) override {
         int nu2, rc;
@@ -578,6 +689,22 @@ int Engine<T>::model_create(double nu, const double* theta, const double* lo, co
     return HBEGP_OK;
 }
 
+// cudaFuncSetAttribute for every GEMM instantiation up front (never inside a stream capture)
+template <typename T>
+static int configure_gemms() {
+#define HBEGP_CFG(BM, BN, WM, WN, AK, BK_)                                                                        \
+    CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<T, BM, BN, WM, WN, AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)GemmCfg<T, BM, BN, WM, WN, AK, BK_>::SMEM_BYTES))
+    HBEGP_CFG(128, 128, 64, 32, true, true);
+    HBEGP_CFG(128, 128, 64, 32, true, false);
+    HBEGP_CFG(128, 128, 64, 32, false, false);
+    HBEGP_CFG(64, 64, 32, 32, true, true);
+    HBEGP_CFG(64, 64, 32, 32, true, false);
+    HBEGP_CFG(64, 64, 32, 32, false, false);
+#undef HBEGP_CFG
+    return HBEGP_OK;
+}
+
 // ------------------------------------------------------------------------------------ restart loop
 static int fit_runs_impl(EngineBase* e, double nu, int n_runs, const double* starts, const double* blo, const double* bhi,
                          int maxeval, hbegp_run_result* results, double* best_theta) {
@@ -676,8 +803,17 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
         if (ce != cudaSuccess) { delete e; return fail(HBEGP_ERR_CUDA, cudaGetErrorString(ce)); }
         e->own_stream = true;
     }
+    {
+        int rc = (dtype == HBEGP_F64) ? configure_gemms<double>() : configure_gemms<float>();
+        if (rc) { delete e; return rc; }
+    }
     int nsub = 4;
-    if (const char* s = getenv("HBEGP_STREAMS")) nsub = std::max(1, std::min(16, atoi(s)));
+    bool forced = false;
+    if (const char* s = getenv("HBEGP_STREAMS")) { nsub = std::max(1, std::min(16, atoi(s))); forced = true; }
+    bool graphs_on = true;
+    if (const char* s = getenv("HBEGP_GRAPHS")) graphs_on = atoi(s) != 0;
+    if (dtype == HBEGP_F64) { static_cast<Engine<double>*>(e)->streams_forced = forced; static_cast<Engine<double>*>(e)->use_graphs = graphs_on; }
+    else { static_cast<Engine<float>*>(e)->streams_forced = forced; static_cast<Engine<float>*>(e)->use_graphs = graphs_on; }
     for (int i = 0; i < nsub; i++) {
         cudaStream_t s;
         cudaEvent_t ev;
@@ -822,6 +958,12 @@ double hbegp_rng_uniform(unsigned long long state[4], double lo, double hi) {
     double v = r.uniform_inclusive(lo, hi);
     std::memcpy(state, r.s, sizeof(r.s));
     return v;
+}
+
+int hbegp_bench_phase(hbegp_ctx* ctx, double nu, int B, const double* theta, int phase, int reps, float* ms_out) {
+    if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");
+    if (ctx->eng->n <= 0) return fail(HBEGP_ERR_INVALID, "no training data: call hbegp_set_data first");
+    return ctx->eng->bench_phase(nu, B, theta, phase, reps, ms_out);
 }
 
 int hbegp_debug_factor(hbegp_ctx* ctx, double nu, const double* theta, void* k, void* w, void* kinv, int* status) {

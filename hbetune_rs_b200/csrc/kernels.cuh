@@ -138,6 +138,25 @@ __global__ void __launch_bounds__(256) k_leaf(T* __restrict__ A, T* __restrict__
         int i = e / TILE, j = e % TILE;
         a[i][j] = (j <= i) ? Ab[(long)i * np + j] : T(0);
     }
+    // Static ownership of the 2080 lower-triangle cells: thread t owns cells t, t + 256, ... (row-major
+    // enumeration e = i (i + 1) / 2 + k), so no index arithmetic is left inside the 64-step loops.
+    constexpr int NCELL = TILE * (TILE + 1) / 2;
+    constexpr int PER = (NCELL + 255) / 256;
+    int ci[PER], ck[PER];
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+        int e = tid + q * 256;
+        if (e < NCELL) {
+            int ii = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+            while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
+            while (ii * (ii + 1) / 2 > e) --ii;
+            ci[q] = ii;
+            ck[q] = e - ii * (ii + 1) / 2;
+        } else {
+            ci[q] = 0;
+            ck[q] = -1;  // never active
+        }
+    }
     // --- right-looking Cholesky; column j stays unscaled in the lower part, L goes to the upper part
     //     transposed (a[j][i] = L[i][j]) so that one barrier per column suffices.
     for (int j = 0; j < TILE; j++) {
@@ -148,17 +167,11 @@ __global__ void __launch_bounds__(256) k_leaf(T* __restrict__ A, T* __restrict__
             dj = T(1);
         }
         const T rs = T(1) / dev_sqrt<T>(dj);
-        const T rd = T(1) / dj;
-        // trailing update of the cells (i, k) with j < k <= i
-        const int rem = TILE - 1 - j;  // rows j+1 .. 63
-        const int cells = rem * (rem + 1) / 2;
-        for (int e = tid; e < cells; e += 256) {
-            int ii = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-            while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
-            while (ii * (ii + 1) / 2 > e) --ii;
-            int kk = e - ii * (ii + 1) / 2;
-            int i = j + 1 + ii, k = j + 1 + kk;
-            a[i][k] -= a[i][j] * a[k][j] * rd;
+        const T rd = rs * rs;
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const int i = ci[q], k = ck[q];
+            if (k > j) a[i][k] -= a[i][j] * a[k][j] * rd;
         }
         if (tid < TILE) {
             if (tid > j) a[j][tid] = a[tid][j] * rs;  // L[tid][j]
@@ -173,22 +186,21 @@ __global__ void __launch_bounds__(256) k_leaf(T* __restrict__ A, T* __restrict__
         else if (j == i) Ab[(long)i * np + j] = T(1) / dinv[i];
     }
     __syncthreads();
-    for (int e = tid; e < TILE * TILE; e += 256) {
-        int i = e / TILE, j = e % TILE;
-        if (j <= i) a[i][j] = (i == j) ? T(1) : T(0);
+#pragma unroll
+    for (int q = 0; q < PER; q++)
+        if (ck[q] >= 0) a[ci[q]][ck[q]] = (ci[q] == ck[q]) ? T(1) : T(0);
+    // --- Gauss-Jordan on [L | I]: rows i > k: W[i][j] -= L[i][k] * (W[k][j] / L[k][k]), j <= k.
+    //     L[i][k] = a[k][i] (upper part), W[i][j] = a[i][j] (lower part); rows are scaled at the end.
+    for (int k = 0; k < TILE - 1; k++) {
+        __syncthreads();
+        const T rk = dinv[k];
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const int i = ci[q], j = ck[q];
+            if (i > k && j <= k && j >= 0) a[i][j] -= a[k][i] * (a[k][j] * rk);
+        }
     }
     __syncthreads();
-    // --- Gauss-Jordan on [L | I]: rows i > k: W[i][j] -= L[i][k] * (W[k][j] / L[k][k]), j <= k.
-    //     L[i][k] = a[k][i] (upper part), W[i][j] = a[i][j] (lower part); row k is scaled at the end.
-    for (int k = 0; k < TILE - 1; k++) {
-        const T rk = dinv[k];
-        const int rows = TILE - 1 - k, cols = k + 1;
-        for (int e = tid; e < rows * cols; e += 256) {
-            int i = k + 1 + e / cols, j = e % cols;
-            a[i][j] -= a[k][i] * (a[k][j] * rk);
-        }
-        __syncthreads();
-    }
     for (int e = tid; e < TILE * TILE; e += 256) {
         int i = e / TILE, j = e % TILE;
         Wb[(long)i * np + j] = (j <= i) ? a[i][j] * dinv[i] : T(0);

@@ -148,7 +148,10 @@ class Context:
         self.dtype = dtype
         self.A = _np_dtype(dtype)
         h = C.c_void_p()
-        check(lib.hbegp_ctx_create(device, dtype, C.c_void_p(stream) if stream else None, C.byref(h)), "hbegp_ctx_create")
+        # stream == 0 is the legacy default stream: pass its explicit handle (cudaStreamLegacy = 0x1), since
+        # NULL asks the library to create its own stream
+        sh = None if stream is None else C.c_void_p(stream if stream != 0 else 1)
+        check(lib.hbegp_ctx_create(device, dtype, sh, C.byref(h)), "hbegp_ctx_create")
         self._h = h
         self.n = self.d = 0
 
@@ -207,6 +210,13 @@ class Context:
         check(lib.hbegp_fit_runs(self._h, nu, R, _ptr(starts), _ptr(lo), _ptr(hi), maxeval, res, _ptr(best_theta)),
               "hbegp_fit_runs")
         return res, best_theta
+
+    def bench_phase(self, theta, phase: int, reps: int = 3, nu: float = 2.5) -> float:
+        """Average milliseconds of a truncated batched evaluation (see hbegp_bench_phase)."""
+        theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        ms = C.c_float()
+        check(lib.hbegp_bench_phase(self._h, nu, theta.shape[0], _ptr(theta), phase, reps, C.byref(ms)), "hbegp_bench_phase")
+        return float(ms.value)
 
     def debug_factor(self, theta, nu: float = 2.5, want=("k", "w", "kinv")):
         theta = np.ascontiguousarray(theta, dtype=np.float64)
