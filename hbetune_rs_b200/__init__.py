@@ -10,4 +10,7 @@ from ._lib import F32, F64, NOT_PD, OK, HbegpError, lib  # noqa: F401
 from .gpr import (BoundedValue, BoundsError, ConstantKernel, Context, FittedKernel, Matern, Model,  # noqa: F401
                   Product, predict)
 
+from .estimator import (LINEAR, LOGARITHMIC, EstimatorGPR, SummaryStatistics, SurrogateModelGPR, YNormalize,  # noqa: F401
+                        estimate_amplitude, expected_improvement)
+
 __version__ = lib.hbegp_version().decode()

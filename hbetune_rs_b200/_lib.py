@@ -24,6 +24,10 @@ class RunResult(C.Structure):
     ]
 
 
+class YNorm(C.Structure):
+    _fields_ = [("amplitude", C.c_double), ("expected", C.c_double), ("projection", C.c_int), ("dtype", C.c_int)]
+
+
 OBJECTIVE_FN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
 
 # name -> (restype, argtypes); must list every symbol include/hbegp.h declares
@@ -53,6 +57,13 @@ PROTOTYPES = {
     "hbegp_rng_seed": (None, [C.c_ulonglong, C.POINTER(C.c_ulonglong)]),
     "hbegp_rng_fork": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "hbegp_rng_uniform": (C.c_double, [C.POINTER(C.c_ulonglong), C.c_double, C.c_double]),
+    "hbegp_ynorm_fit": (C.c_int, [C.c_int, C.c_int, C.c_long, C.c_void_p, C.POINTER(C.c_double), C.c_void_p,
+                                  C.POINTER(YNorm)]),
+    "hbegp_ynorm_apply": (C.c_int, [C.POINTER(YNorm), C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hbegp_estimate_amplitude": (C.c_int, [C.c_int, C.c_long, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "hbegp_expected_improvement": (C.c_double, [C.c_double, C.c_double, C.c_double]),
+    "hbegp_expected_improvement_a": (C.c_int, [C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
+    "hbegp_normal_inverse_cdf": (C.c_double, [C.c_double, C.c_double, C.c_double]),
     "hbegp_bench_phase": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                     C.POINTER(C.c_float)]),
     "hbegp_debug_factor": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -56,11 +56,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-template <typename T, int BM, int BN, int WM, int WN, bool A_KMAJOR, bool B_KMAJOR>
+template <typename T, int BM, int BN, int WM, int WN, bool A_KMAJOR, bool B_KMAJOR, int BK_ = 16, int STAGES_ = 3>
 struct GemmCfg {
-    static constexpr int BK = 16;
+    static constexpr int BK = BK_;
     static constexpr int PAD = 4;
-    static constexpr int STAGES = 3;
+    static constexpr int STAGES = STAGES_;
     static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
     static constexpr int THREADS = WARPS_M * WARPS_N * 32;
     static constexpr int VEC = 16 / sizeof(T);
@@ -96,10 +96,10 @@ __device__ __forceinline__ void load_tile(T* __restrict__ s, const T* __restrict
     }
 }
 
-template <typename T, int BM, int BN, int WM, int WN, bool A_KMAJOR, bool B_KMAJOR>
-__global__ void __launch_bounds__(GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR>::THREADS)
+template <typename T, int BM, int BN, int WM, int WN, bool A_KMAJOR, bool B_KMAJOR, int BK_ = 16, int STAGES_ = 3>
+__global__ void __launch_bounds__(GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR, BK_, STAGES_>::THREADS)
     gemm_kernel(const GemmArgs<T> p) {
-    using Cfg = GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR>;
+    using Cfg = GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR, BK_, STAGES_>;
     constexpr int BK = Cfg::BK, STAGES = Cfg::STAGES, THREADS = Cfg::THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* smem = reinterpret_cast<T*>(smem_raw);
@@ -290,16 +290,23 @@ inline cudaError_t launch_gemm_cfg(const GemmArgs<T>& a, int batch, cudaStream_t
     return cudaGetLastError();
 }
 
-// Picks the CTA tile: 128x128 (8 warps, 64x32 warp tiles) when the problem tiles evenly and is large
-// enough to fill the machine, else 64x64 (4 warps, 32x32 warp tiles).
+// CTA tile choice.  Measured on B200 (probes/gemm_bench.cu, profiles/r01_gemm_tile_probe.log): the 64x64 tile
+// (4 warps, 32x32 warp tiles, 60 KB of shared memory -> 3 CTAs per SM) sustains 33.2 TFLOP/s on 2048^3 x 4
+// against 31.0 for 128x128 (8 warps, 1 CTA per SM) and 35.6 for cuBLAS, and it quantises far better on the
+// small and triangular grids of the recursion, so it is the default; HBEGP_TILE=128 selects the large tile
+// where a problem tiles evenly.
+inline int& gemm_tile_pref() {
+    static int pref = 64;
+    return pref;
+}
+
+inline int pick_gemm_tile(int M, int N) {
+    return (gemm_tile_pref() == 128 && M % 128 == 0 && N % 128 == 0) ? 128 : 64;
+}
+
 template <typename T, bool AK, bool BK_>
-inline cudaError_t launch_gemm(const GemmArgs<T>& a, int batch, cudaStream_t stream, int force_tile = 0) {
-    bool can128 = (a.M % 128 == 0) && (a.N % 128 == 0);
-    long tiles128 = can128 ? (a.lower_only ? (long)(a.M / 128) * (a.M / 128 + 1) / 2 : (long)(a.M / 128) * (a.N / 128)) : 0;
-    bool use128 = can128 && tiles128 * batch >= 148;
-    if (force_tile == 64) use128 = false;
-    if (force_tile == 128 && can128) use128 = true;
-    if (use128) return launch_gemm_cfg<T, 128, 128, 64, 32, AK, BK_>(a, batch, stream);
+inline cudaError_t launch_gemm(const GemmArgs<T>& a, int batch, cudaStream_t stream) {
+    if (pick_gemm_tile(a.M, a.N) == 128) return launch_gemm_cfg<T, 128, 128, 64, 32, AK, BK_>(a, batch, stream);
     return launch_gemm_cfg<T, 64, 64, 32, 32, AK, BK_>(a, batch, stream);
 }
 

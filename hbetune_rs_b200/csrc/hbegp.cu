@@ -23,6 +23,7 @@
 #include "gemm.cuh"
 #include "kernels.cuh"
 #include "lbfgs.h"
+#include "adapter.h"
 
 namespace hbegp {
 
@@ -571,7 +572,7 @@ struct ModelT : Model {
             return HBEGP_OK;
         }
         const int chunk = (int)std::min<long>(predict_chunk_rows(), round_up(m, 128));
-        const int bn = (np % 128 == 0) ? 128 : 64;
+        const int bn = pick_gemm_tile(128, np);  // rows are always a multiple of 128
         const int ntile = np / bn;
         int rc;
         if ((rc = kstar.ensure((size_t)chunk * np * sizeof(T)))) return rc;
@@ -589,7 +590,7 @@ struct ModelT : Model {
             g.M = rows; g.N = np; g.K = np; g.kmode = K_LE_N; g.lower_only = 0;
             g.alpha = T(1); g.beta = T(0);
             g.rowsumsq = (T*)part.p; g.ld_rs = ntile; g.s_rs = 0;
-            CUDA_TRY((launch_gemm<T, true, true>(g, 1, st, bn)));
+            CUDA_TRY((launch_gemm<T, true, true>(g, 1, st)));
             e->launches++;
             k_var_finish<T><<<(rows + 255) / 256, 256, 0, st>>>((const T*)part.p, ntile, ntile, rows, m, row0, (T)c, var, nb);
             e->launches++;
@@ -778,6 +779,34 @@ struct hbegp_model {
     Model* m;
 };
 
+template <typename A>
+static int ynorm_fit_t(int projection, long n, const A* y, const double* ko, A* out_y, hbegp_ynorm* out) {
+    YNorm<A> yn;
+    yn.fit(projection, y, n, ko != nullptr, ko ? (A)*ko : A(0), out_y);
+    out->amplitude = (double)yn.amplitude;
+    out->expected = (double)yn.expected;
+    out->projection = projection;
+    return HBEGP_OK;
+}
+
+template <typename A>
+static int ynorm_apply_t(const hbegp_ynorm* h, int op, long n, const A* a, const A* b, A* out) {
+    YNorm<A> yn;
+    yn.amplitude = (A)h->amplitude;
+    yn.expected = (A)h->expected;
+    yn.projection = h->projection;
+    for (long i = 0; i < n; i++) {
+        switch (op) {
+            case 0: out[i] = yn.into(a[i]); break;
+            case 1: out[i] = yn.location_from(a[i]); break;
+            case 2: out[i] = yn.mean_from(a[i], b[i]); break;
+            case 3: out[i] = yn.std_from(a[i], b[i]); break;
+            default: out[i] = yn.cv_from(a[i], b[i]); break;
+        }
+    }
+    return HBEGP_OK;
+}
+
 extern "C" {
 
 const char* hbegp_version(void) { return "hbegp 0.1.0 (sm_100a)"; }
@@ -810,6 +839,7 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
     int nsub = 4;
     bool forced = false;
     if (const char* s = getenv("HBEGP_STREAMS")) { nsub = std::max(1, std::min(16, atoi(s))); forced = true; }
+    if (const char* s = getenv("HBEGP_TILE")) gemm_tile_pref() = (atoi(s) == 128) ? 128 : 64;
     bool graphs_on = true;
     if (const char* s = getenv("HBEGP_GRAPHS")) graphs_on = atoi(s) != 0;
     if (dtype == HBEGP_F64) { static_cast<Engine<double>*>(e)->streams_forced = forced; static_cast<Engine<double>*>(e)->use_graphs = graphs_on; }
@@ -959,6 +989,49 @@ double hbegp_rng_uniform(unsigned long long state[4], double lo, double hi) {
     std::memcpy(state, r.s, sizeof(r.s));
     return v;
 }
+
+int hbegp_ynorm_fit(int dtype, int projection, long n, const void* y, const double* known_optimum, void* y_out,
+                    hbegp_ynorm* out) {
+    if (n <= 0 || !y || !y_out || !out || (projection != HBEGP_PROJ_LINEAR && projection != HBEGP_PROJ_LOG))
+        return fail(HBEGP_ERR_INVALID, "ynorm_fit: bad arguments");
+    out->dtype = dtype;
+    if (dtype == HBEGP_F64) return ynorm_fit_t<double>(projection, n, (const double*)y, known_optimum, (double*)y_out, out);
+    if (dtype == HBEGP_F32) return ynorm_fit_t<float>(projection, n, (const float*)y, known_optimum, (float*)y_out, out);
+    return fail(HBEGP_ERR_INVALID, "ynorm_fit: bad dtype");
+}
+
+int hbegp_ynorm_apply(const hbegp_ynorm* yn, int op, long n, const void* a, const void* b, void* out) {
+    if (!yn || n < 0 || op < 0 || op > 4 || (n > 0 && (!a || !out)) || (op >= 2 && n > 0 && !b))
+        return fail(HBEGP_ERR_INVALID, "ynorm_apply: bad arguments");
+    if (yn->dtype == HBEGP_F64) return ynorm_apply_t<double>(yn, op, n, (const double*)a, (const double*)b, (double*)out);
+    return ynorm_apply_t<float>(yn, op, n, (const float*)a, (const float*)b, (float*)out);
+}
+
+int hbegp_estimate_amplitude(int dtype, long n, const void* y, const double* bounds, double out[3]) {
+    if (n <= 0 || !y || !out) return fail(HBEGP_ERR_INVALID, "estimate_amplitude: bad arguments");
+    if (dtype == HBEGP_F64) estimate_amplitude<double>((const double*)y, n, bounds, out);
+    else estimate_amplitude<float>((const float*)y, n, bounds, out);
+    if (!(out[1] <= out[0] && out[0] <= out[2])) return fail(HBEGP_ERR_INVALID, "estimate_amplitude: start outside bounds (gpr.rs:449 unwrap)");
+    return HBEGP_OK;
+}
+
+double hbegp_expected_improvement(double mean, double std, double fmin) { return expected_improvement(mean, std, fmin); }
+
+int hbegp_expected_improvement_a(int dtype, long m, const void* mean, const void* var, double fmin, void* ei_out) {
+    if (m < 0 || (m > 0 && (!mean || !var || !ei_out))) return fail(HBEGP_ERR_INVALID, "expected_improvement_a: bad arguments");
+    if (dtype == HBEGP_F64) {
+        const double *mu = (const double*)mean, *v = (const double*)var;
+        double* o = (double*)ei_out;
+        for (long i = 0; i < m; i++) o[i] = expected_improvement(mu[i], std::sqrt(v[i]), fmin);
+    } else {
+        const float *mu = (const float*)mean, *v = (const float*)var;
+        float* o = (float*)ei_out;
+        for (long i = 0; i < m; i++) o[i] = (float)expected_improvement((double)mu[i], (double)std::sqrt(v[i]), fmin);
+    }
+    return HBEGP_OK;
+}
+
+double hbegp_normal_inverse_cdf(double p, double mean, double std) { return mean + std * norm_ppf(p); }
 
 int hbegp_bench_phase(hbegp_ctx* ctx, double nu, int B, const double* theta, int phase, int reps, float* ms_out) {
     if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");

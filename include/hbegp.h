@@ -127,6 +127,34 @@ void hbegp_rng_seed(unsigned long long seed, unsigned long long state[4]);
 void hbegp_rng_fork(unsigned long long state[4], unsigned long long child[4]);
 double hbegp_rng_uniform(unsigned long long state[4], double lo, double hi);
 
+/* ---- adapter pieces around src/gpr (host-side, no GPU) --------------------------------------------- */
+#define HBEGP_PROJ_LINEAR 0
+#define HBEGP_PROJ_LOG 1
+/* YNormalize (src/core/ynormalize.rs:7-12): amplitude / expected hold values of the data type `dtype`. */
+typedef struct hbegp_ynorm {
+    double amplitude;
+    double expected;
+    int projection;
+    int dtype;
+} hbegp_ynorm;
+/* YNormalize::new_project_into_normalized (ynormalize.rs:162-195); known_optimum may be NULL. */
+int hbegp_ynorm_fit(int dtype, int projection, long n, const void* y, const double* known_optimum,
+                    void* y_normalized_out, hbegp_ynorm* out);
+/* op 0: project_into_normalized(a)            (ynormalize.rs:197-210)
+ * op 1: project_location_from_normalized(a)   (:215-225)
+ * op 2: project_mean_from_normalized(a = mean, b = variance)   (:227-247)
+ * op 3: project_std_from_normalized(a = mean, b = variance)    (:249-267)
+ * op 4: project_cv_from_normalized(a = mean, b = variance)     (:269-288) */
+int hbegp_ynorm_apply(const hbegp_ynorm* yn, int op, long n, const void* a, const void* b, void* out);
+/* estimate_amplitude (src/core/gpr.rs:429-450): out = {start, lo, hi}; bounds (2 values) may be NULL. */
+int hbegp_estimate_amplitude(int dtype, long n, const void* y, const double* bounds, double out[3]);
+/* expected_improvement (src/core/acquisition.rs:141-171), f64; NaN where the reference would panic. */
+double hbegp_expected_improvement(double mean, double std, double fmin);
+/* The per-row loop of predict_mean_ei_a (src/core/gpr.rs:198-208): ei[i] = EI(mean[i], sqrt(var[i]), fmin). */
+int hbegp_expected_improvement_a(int dtype, long m, const void* mean, const void* var, double fmin, void* ei_out);
+/* statrs Normal::inverse_cdf as used for the quartiles of predict_statistics (src/core/gpr.rs:140-166). */
+double hbegp_normal_inverse_cdf(double p, double mean, double std);
+
 /* ---- debugging / parity aids -------------------------------------------------------------------- */
 /* Copies out intermediates of ONE evaluation at theta (any pointer may be NULL): k[n*n] lower triangle of
  * K + noise I (upper = 0), w[n*n] = L^-1 (the inverse Cholesky factor; L itself is consumed by the fused

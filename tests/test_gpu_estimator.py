@@ -1,0 +1,99 @@
+"""EstimatorGPR / SurrogateModelGPR (src/core/gpr.rs) on the GPU against the oracle's adapter restatement,
+both driven by the same bounded L-BFGS and the same RNG stream (seeded like tests/gpr_tests.rs)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import adapter as oad
+from oracle.rng import RNG
+from tests.util import lib_minimizer
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, d, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, d))
+    y = ((x - 0.4) ** 2).sum(axis=1) * 30 + 5 + 0.3 * rng.standard_normal(n)  # noisy sphere, natural units
+    return x, y
+
+
+@pytest.mark.parametrize("proj", ["linear", "logarithmic"])
+def test_estimate_predict_extend_match_oracle(proj):
+    import hbetune_rs_b200 as h
+    n, d = 80, 2
+    x, y = _data(n, d, 4531)
+    est = h.EstimatorGPR(d).with_noise_bounds(1e-2, 1e1).n_restarts_optimizer(1)
+    est.y_projection(h.LINEAR if proj == "linear" else h.LOGARITHMIC)
+    oest = oad.EstimatorGPR(d)
+    oest.noise_bounds, oest.n_restarts_optimizer, oest.y_projection = (1e-2, 1e1), 1, proj
+    model = est.estimate(x, y, None, RNG.new_with_seed(123), want_kinv=True)
+    omodel = oest.estimate(x, y, None, RNG.new_with_seed(123), lib_minimizer())
+    assert abs(model.lml - omodel.lml) <= 1e-7 * abs(omodel.lml)
+    np.testing.assert_allclose(model.length_scales(), omodel.length_scales(), rtol=1e-4)
+    xs = np.random.default_rng(9).random((40, d))
+    np.testing.assert_allclose(model.predict_mean_a(xs), omodel.predict_mean_a(xs), rtol=1e-6)
+    fmin = float(y.min())
+    mean, ei = model.predict_mean_ei_a(xs, fmin)
+    omean, oei = omodel.predict_mean_ei_a(xs, fmin)
+    np.testing.assert_allclose(mean, omean, rtol=1e-6)
+    np.testing.assert_allclose(ei, oei, rtol=1e-4, atol=1e-9)
+    assert (ei >= 0).all()
+    m1, e1 = model.predict_mean_ei(xs[3], fmin)
+    assert m1 == mean[3] and e1 == ei[3]
+    assert model.predict_mean(xs[5]) == pytest.approx(omodel.predict_mean_a(xs[5:6])[0], rel=1e-6)
+    assert model.predict_confidence_bound(xs[0], 1.5) == pytest.approx(omodel.predict_confidence_bound(xs[0], 1.5), rel=1e-5)
+    st = model.predict_statistics(xs[0])
+    assert st.q1 < st.q2 < st.q3 and st.std > 0 and st.iqr() == st.q3 - st.q1
+    if proj == "linear":
+        assert st.q2 == pytest.approx(st.mean, rel=1e-12)  # symmetric in natural units
+        assert st.cv == pytest.approx(st.std / st.mean, rel=1e-12)
+    # extend: same theta, more data, no optimisation (gpr.rs:293-337, fit.rs:33-68)
+    x2, y2 = _data(n + 10, d, 77)
+    ext = est.extend(x2, y2, model)
+    oext = oest.extend(x2, y2, omodel)
+    assert ext.length_scales() == model.length_scales()
+    assert ext.lml == pytest.approx(oext.lml, rel=1e-6)
+    np.testing.assert_allclose(ext.predict_mean_a(xs), oext.predict_mean_a(xs), rtol=1e-6)
+    # prior reuse: estimate() starting from the prior's kernel and noise (gpr.rs:402-409)
+    again = est.estimate(x2, y2, ext, RNG.new_with_seed(5))
+    assert again.lml >= ext.lml - 1e-9
+
+
+def test_bounds_errors_surface_like_the_reference():
+    import hbetune_rs_b200 as h
+    x, y = _data(20, 2, 1)
+    with pytest.raises(h.estimator.NoiseBounds):
+        h.EstimatorGPR(2).with_noise_bounds(2.0, 5.0).estimate(x, y, None, RNG.new_with_seed(1))  # start 1.0 not in bounds
+    with pytest.raises(h.estimator.LengthScaleBounds):
+        h.EstimatorGPR(2).with_length_scale_bounds([(2.0, 1.0)] * 2).estimate(x, y, None, RNG.new_with_seed(1))
+
+
+def test_fit_f32_close_to_f64():
+    """--use-32 (main.rs:240-244): f32 data and linear algebra, f64 hyper-parameters.  The two fits walk
+    different trajectories, so this is a behavioural check (like tests/gpr_tests.rs), not parity."""
+    import hbetune_rs_b200 as h
+    x, y = _data(100, 2, 9372)
+    xs = np.random.default_rng(0).random((30, 2))
+    preds = {}
+    for A in (np.float64, np.float32):
+        est = h.EstimatorGPR(2, dtype=A).with_noise_bounds(1e-2, 1e1).n_restarts_optimizer(1)
+        model = est.estimate(x.astype(A), y.astype(A), None, RNG.new_with_seed(123))
+        preds[A] = model.predict_mean_a(xs.astype(A))
+        assert preds[A].dtype == A
+    assert np.abs(preds[np.float32] - preds[np.float64]).max() < 0.05 * np.abs(preds[np.float64]).max()
+
+
+def test_gpr_behaviour_1d_like_reference_suite():
+    """tests/gpr_tests.rs:72-225 style: a 1-D fit reproduces its data and is more certain near data."""
+    import hbetune_rs_b200 as h
+    xs = np.array([0.1, 0.5, 0.5, 0.9])[:, None]
+    ys = np.array([1.0, 1.8, 2.2, 3.0])
+    est = h.EstimatorGPR(1).with_noise_bounds(1e-3, 1e1).n_restarts_optimizer(2)
+    model = est.estimate(xs, ys, None, RNG.new_with_seed(123))
+    got = model.predict_mean_a(np.array([[0.1], [0.5], [0.9]]))
+    np.testing.assert_allclose(got, [1.0, 2.0, 3.0], atol=0.15)
+    near = model.predict_statistics(np.array([0.5])).std
+    far = model.predict_statistics(np.array([0.0])).std
+    assert near < far
