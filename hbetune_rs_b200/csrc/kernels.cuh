@@ -121,90 +121,148 @@ __global__ void __launch_bounds__(256) k_assemble(const T* __restrict__ xsT, int
         }
 }
 
+// Reciprocal of a Cholesky pivot.  It sits on the 64-step critical path of the leaf, where an IEEE FP64
+// division costs ~8 dependent FP64 operations; a single-precision seed plus two Newton steps (4 dependent
+// DFMAs, relative error ~2^-52 for pivots inside the float range) halves that.
+template <typename T>
+__device__ __forceinline__ T pivot_rcp(T d);
+template <>
+__device__ __forceinline__ float pivot_rcp<float>(float d) { return 1.0f / d; }
+template <>
+__device__ __forceinline__ double pivot_rcp<double>(double d) {
+    if (!(d > 1e-30 && d < 1e30)) return 1.0 / d;
+    double r = (double)__frcp_rn((float)d);
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
 // Leaf of the recursive factorisation: 64x64 diagonal block at (r0, r0).  In: A block (lower part).
 // Out: L in the lower part of the A block, W = L^-1 as a full tile (zeros above the diagonal) in the
 // W buffer, sum_i ln L_ii in ldp[b][leaf], status[b] = 1 when a pivot is not positive (lml.rs:47-50).
-template <typename T>
+//
+// 16 x 16 threads; thread (tx, ty) keeps the 4 x 4 cells (ty + 16a, tx + 16q) in registers.  Both phases
+// are 64 sequential rank-1 steps with one barrier each: per step a thread gathers 4 + 4 operands from
+// shared memory and updates its live cells; only the cells another thread needs next (the next pivot
+// column / row) are written back to shared memory.
+template <typename T, int DBG = 0>  // DBG: probe-only switches (1: skip Cholesky loop, 2: skip Gauss-Jordan loop, 3: both)
 __global__ void __launch_bounds__(256) k_leaf(T* __restrict__ A, T* __restrict__ W, long mstride, int np, int r0,
                                               T* __restrict__ ldp, int ldp_stride, int* __restrict__ status) {
-    __shared__ T a[TILE][TILE + 1];
+    __shared__ T as[TILE][TILE + 1];
     __shared__ T dinv[TILE];
     __shared__ int fail;
-    const int b = blockIdx.z, tid = threadIdx.x;
+    const int b = blockIdx.z, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     T* Ab = A + (long)b * mstride + (long)r0 * np + r0;
     T* Wb = W + (long)b * mstride + (long)r0 * np + r0;
     if (tid == 0) fail = 0;
-    for (int e = tid; e < TILE * TILE; e += 256) {
-        int i = e / TILE, j = e % TILE;
-        a[i][j] = (j <= i) ? Ab[(long)i * np + j] : T(0);
-    }
-    // Static ownership of the 2080 lower-triangle cells: thread t owns cells t, t + 256, ... (row-major
-    // enumeration e = i (i + 1) / 2 + k), so no index arithmetic is left inside the 64-step loops.
-    constexpr int NCELL = TILE * (TILE + 1) / 2;
-    constexpr int PER = (NCELL + 255) / 256;
-    int ci[PER], ck[PER];
+    T v[4][4];
 #pragma unroll
-    for (int q = 0; q < PER; q++) {
-        int e = tid + q * 256;
-        if (e < NCELL) {
-            int ii = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-            while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
-            while (ii * (ii + 1) / 2 > e) --ii;
-            ci[q] = ii;
-            ck[q] = e - ii * (ii + 1) / 2;
-        } else {
-            ci[q] = 0;
-            ck[q] = -1;  // never active
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = ty + 16 * a, k = tx + 16 * q;
+            v[a][q] = (k <= i) ? Ab[(long)i * np + k] : T(0);
+            as[i][k] = v[a][q];
         }
-    }
-    // --- right-looking Cholesky; column j stays unscaled in the lower part, L goes to the upper part
-    //     transposed (a[j][i] = L[i][j]) so that one barrier per column suffices.
-    for (int j = 0; j < TILE; j++) {
+    // --- right-looking Cholesky on unscaled columns: a_ik -= a_ij a_kj / a_jj; L[i][j] = a_ij / sqrt(a_jj)
+    //     goes to the upper part transposed (as[j][i]).
+    for (int j = 0; j < ((DBG & 1) ? 0 : TILE); j++) {
         __syncthreads();
-        T dj = a[j][j];
+        T dj = as[j][j];
         if (!(dj > T(0)) || !(dj <= T(1e300))) {
             if (tid == 0) fail = 1;
             dj = T(1);
         }
-        const T rs = T(1) / dev_sqrt<T>(dj);
-        const T rd = rs * rs;
+        const T rd = pivot_rcp<T>(dj);
+        T li[4], lk[4];
 #pragma unroll
-        for (int q = 0; q < PER; q++) {
-            const int i = ci[q], k = ck[q];
-            if (k > j) a[i][k] -= a[i][j] * a[k][j] * rd;
-        }
-        if (tid < TILE) {
-            if (tid > j) a[j][tid] = a[tid][j] * rs;  // L[tid][j]
-            if (tid == j) dinv[j] = rs;               // 1 / L[j][j]
+        for (int a = 0; a < 4; a++) li[a] = as[ty + 16 * a][j];
+#pragma unroll
+        for (int q = 0; q < 4; q++) lk[q] = as[tx + 16 * q][j];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (j < 16 * q + 15) {  // block column still has live cells (uniform branch)
+#pragma unroll
+                for (int a = q; a < 4; a++) {
+                    // branch-free: a select and a predicated store (divergent branch regions cost ~30 cycles each)
+                    const int i = ty + 16 * a, k = tx + 16 * q;
+                    const bool act = (k > j) & (k <= i);
+                    // the operand product does not wait for the pivot reciprocal: chain = rcp -> one FMA
+                    const T upd = fma(-(li[a] * lk[q]), rd, v[a][q]);
+                    v[a][q] = act ? upd : v[a][q];
+                    if (act & (k == j + 1)) as[i][k] = upd;  // next pivot column
+                }
+            }
         }
     }
     __syncthreads();
-    // --- the lower part is dead now: write L back, then reuse it (with the diagonal) for W = L^-1
-    for (int e = tid; e < TILE * TILE; e += 256) {
-        int i = e / TILE, j = e % TILE;
-        if (j < i) Ab[(long)i * np + j] = a[j][i];
-        else if (j == i) Ab[(long)i * np + j] = T(1) / dinv[i];
+    // The unscaled columns are final: scale them into L off the critical path (the square roots of all
+    // 64 pivots in parallel), L^T into the upper part: as[j][i] = L[i][j].
+    if (tid < TILE) {
+        T dj = as[tid][tid];
+        if (!(dj > T(0)) || !(dj <= T(1e300))) dj = T(1);
+        dinv[tid] = T(1) / dev_sqrt<T>(dj);  // 1 / L[j][j]
     }
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < PER; q++)
-        if (ck[q] >= 0) a[ci[q]][ck[q]] = (ci[q] == ck[q]) ? T(1) : T(0);
-    // --- Gauss-Jordan on [L | I]: rows i > k: W[i][j] -= L[i][k] * (W[k][j] / L[k][k]), j <= k.
-    //     L[i][k] = a[k][i] (upper part), W[i][j] = a[i][j] (lower part); rows are scaled at the end.
-    for (int k = 0; k < TILE - 1; k++) {
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = ty + 16 * a, k = tx + 16 * q;
+            if (k < i) as[k][i] = as[i][k] * dinv[k];
+        }
+    __syncthreads();
+    // --- L back to global (from the upper part), then W = L^-1 in the registers / lower part
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = ty + 16 * a, k = tx + 16 * q;
+            if (k < i) Ab[(long)i * np + k] = as[k][i];
+            else if (k == i) Ab[(long)i * np + k] = T(1) / dinv[i];
+        }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = ty + 16 * a, k = tx + 16 * q;
+            v[a][q] = (i == k) ? T(1) : T(0);
+            if (k <= i) as[i][k] = v[a][q];
+        }
+    // --- Gauss-Jordan on [L | I]: rows i > k: W[i][j] -= L[i][k] * (W[k][j] / L[k][k]) for j <= k.
+    //     L[i][k] = as[k][i] (upper part), row k of W = as[k][0..k]; rows are scaled by 1/L[i][i] at the end.
+    for (int k = 0; k < ((DBG & 2) ? 0 : TILE - 1); k++) {
         __syncthreads();
         const T rk = dinv[k];
+        T li[4], wk[4];
 #pragma unroll
-        for (int q = 0; q < PER; q++) {
-            const int i = ci[q], j = ck[q];
-            if (i > k && j <= k && j >= 0) a[i][j] -= a[k][i] * (a[k][j] * rk);
+        for (int a = 0; a < 4; a++) li[a] = as[k][ty + 16 * a];
+#pragma unroll
+        for (int q = 0; q < 4; q++) wk[q] = as[k][tx + 16 * q] * rk;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            if (k < 16 * a + 15) {  // block row still has rows below k (uniform branch)
+#pragma unroll
+                for (int q = 0; q <= a; q++) {
+                    const int i = ty + 16 * a, jj = tx + 16 * q;
+                    const bool act = (i > k) & (jj <= k);
+                    const T upd = fma(-li[a], wk[q], v[a][q]);
+                    v[a][q] = act ? upd : v[a][q];
+                    if (act & (i == k + 1)) as[i][jj] = upd;  // next pivot row
+                }
+            }
         }
     }
-    __syncthreads();
-    for (int e = tid; e < TILE * TILE; e += 256) {
-        int i = e / TILE, j = e % TILE;
-        Wb[(long)i * np + j] = (j <= i) ? a[i][j] * dinv[i] : T(0);
-    }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = ty + 16 * a, k = tx + 16 * q;
+            Wb[(long)i * np + k] = (k <= i) ? v[a][q] * dinv[i] : T(0);
+        }
     if (tid < 32) {
         T s = T(0);
         for (int i = tid; i < TILE; i += 32) s += -dev_log<T>(dinv[i]);
