@@ -38,6 +38,9 @@ struct GemmArgs {
     T alpha, beta;
     T* rowsumsq;  // if non-null: partial[(row) * ld_rs + tile_n] = sum_j acc(row, j)^2, C untouched
     long ld_rs, s_rs;
+    // K_LE_N only: rasterise in groups of `raster_group` row tiles (all column tiles of a group before the
+    // next group) so that the group's A rows stay in L2 while B streams; 0 = plain column-major order.
+    int raster_group;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -124,6 +127,13 @@ __global__ void __launch_bounds__(GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR,
         } else if (p.kmode == K_LE_M) {
             mt = tiles_m - 1 - t / tiles_n;
             nt = t % tiles_n;
+        } else if (p.kmode == K_LE_N && p.raster_group > 0) {
+            const int per_group = p.raster_group * tiles_n;
+            const int g = t / per_group, base = g * p.raster_group;
+            const int gsize = min(p.raster_group, tiles_m - base);
+            const int r = t - g * per_group;
+            nt = tiles_n - 1 - r / gsize;
+            mt = base + r % gsize;
         } else if (p.kmode == K_LE_N) {
             nt = tiles_n - 1 - t / tiles_m;
             mt = t % tiles_m;

@@ -100,6 +100,7 @@ struct Model {
     void release_all() {
         W.release(); alpha.release(); xsT.release(); ls.release();
         kstar.release(); part.release(); nbelow.release(); xs_tmp.release(); mean_tmp.release(); var_tmp.release();
+        acq1.release(); acq2.release(); argv.release(); argi.release();
     }
     virtual ~Model() {
         release_all();
@@ -107,6 +108,9 @@ struct Model {
     }
     virtual int predict_device(long m, const void* xs, void* mean, void* var, long* n_below_device) = 0;
     virtual int predict_host(long m, const void* xs, void* mean, void* var, long* n_below) = 0;
+    virtual int predict_acquisition(int mode, const hbegp_ynorm* yn, long m, const void* xs, double param, void* out1,
+                                    void* out2, long* best, long* n_below) = 0;
+    DevBuf acq1, acq2, argv, argi;
 };
 
 static int nu_to_nu2(double nu, int* nu2) {
@@ -590,6 +594,8 @@ struct ModelT : Model {
             g.M = rows; g.N = np; g.K = np; g.kmode = K_LE_N; g.lower_only = 0;
             g.alpha = T(1); g.beta = T(0);
             g.rowsumsq = (T*)part.p; g.ld_rs = ntile; g.s_rs = 0;
+            // keep ~48 MB of k* rows resident in L2 while W streams (ncu before: 35 GB of DRAM reads per 1 GB chunk)
+            g.raster_group = (int)std::max<size_t>(1, ((size_t)48 << 20) / ((size_t)bn * np * sizeof(T)));
             CUDA_TRY((launch_gemm<T, true, true>(g, 1, st)));
             e->launches++;
             k_var_finish<T><<<(rows + 255) / 256, 256, 0, st>>>((const T*)part.p, ntile, ntile, rows, m, row0, (T)c, var, nb);
@@ -612,6 +618,9 @@ struct ModelT : Model {
         if (nu2 == 3) return predict_impl<3>(m, (const T*)xs, (T*)mean, (T*)var, nb);
         return predict_impl<1>(m, (const T*)xs, (T*)mean, (T*)var, nb);
     }
+
+    int predict_acquisition(int mode, const hbegp_ynorm* yn, long m, const void* xs, double param, void* out1, void* out2,
+                            long* best, long* n_below) override;
 
     int predict_host(long m, const void* xs, void* mean, void* var, long* n_below) override {
         if (m < 0 || (m > 0 && (!xs || !mean))) return fail(HBEGP_ERR_INVALID, "predict: bad arguments");
@@ -636,6 +645,58 @@ struct ModelT : Model {
         return HBEGP_OK;
     }
 };
+
+// predict + acquisition epilogue + arg-best, all on the device; only the requested vectors come back
+template <typename T>
+int ModelT<T>::predict_acquisition(int mode, const hbegp_ynorm* yn, long m, const void* xs, double param, void* out1,
+                                   void* out2, long* best, long* n_below) {
+    if (!yn || m < 0 || (m > 0 && !xs) || (mode != 0 && mode != 1)) return fail(HBEGP_ERR_INVALID, "predict_acquisition: bad arguments");
+    if (best) *best = -1;
+    if (n_below) *n_below = 0;
+    if (m == 0) return HBEGP_OK;
+    Engine<T>* e = static_cast<Engine<T>*>(eng);
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    int rc;
+    if ((rc = xs_tmp.ensure((size_t)m * d * sizeof(T)))) return rc;
+    if ((rc = mean_tmp.ensure((size_t)m * sizeof(T)))) return rc;
+    if ((rc = var_tmp.ensure((size_t)m * sizeof(T)))) return rc;
+    if ((rc = acq1.ensure((size_t)m * sizeof(T)))) return rc;
+    if ((rc = acq2.ensure((size_t)m * sizeof(T)))) return rc;
+    const int nparts = (int)std::min<long>(1024, (m + 255) / 256);
+    if ((rc = argv.ensure((size_t)nparts * sizeof(T)))) return rc;
+    if ((rc = argi.ensure((size_t)(nparts + 1) * sizeof(long)))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(xs_tmp.p, xs, (size_t)m * d * sizeof(T), cudaMemcpyHostToDevice, st));
+    if ((rc = predict_device(m, xs_tmp.p, mean_tmp.p, var_tmp.p, nullptr))) return rc;
+    YNorm<T> y;
+    y.amplitude = (T)yn->amplitude;
+    y.expected = (T)yn->expected;
+    y.projection = yn->projection;
+    double fmin_n = 0.0;
+    T cb = T(0);
+    if (mode == 0) fmin_n = (double)y.into((T)param);  // gpr.rs:192-196: fmin projected into normalised space in A
+    else cb = (T)param;
+    k_acquisition<T><<<(unsigned)((m + 255) / 256), 256, 0, st>>>((const T*)mean_tmp.p, (const T*)var_tmp.p, m, mode, y.projection,
+                                                                 y.amplitude, y.expected, fmin_n, cb, (T*)acq1.p, (T*)acq2.p);
+    e->launches++;
+    const T* key = (mode == 0) ? (const T*)acq2.p : (const T*)acq1.p;
+    long hbest = -1;
+    if (best) {
+        k_argbest_part<T><<<nparts, 256, 0, st>>>(key, m, mode == 0 ? 1 : 0, (T*)argv.p, (long*)argi.p);
+        k_argbest_final<T><<<1, 32, 0, st>>>((const T*)argv.p, (const long*)argi.p, nparts, mode == 0 ? 1 : 0, (long*)argi.p + nparts);
+        e->launches += 2;
+        CUDA_TRY(cudaMemcpyAsync(&hbest, (long*)argi.p + nparts, sizeof(long), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (out1) CUDA_TRY(cudaMemcpyAsync(out1, acq1.p, (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, st));
+    if (out2 && mode == 0) CUDA_TRY(cudaMemcpyAsync(out2, acq2.p, (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, st));
+    unsigned long long hb = 0;
+    CUDA_TRY(cudaMemcpyAsync(&hb, nbelow.p, sizeof(hb), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (best) *best = hbest;
+    if (n_below) *n_below = (long)hb;
+    return HBEGP_OK;
+}
 
 template <typename T>
 int Engine<T>::model_create(double nu, const double* theta, const double* lo, const double* hi, Model** out, double* lml,
@@ -956,6 +1017,20 @@ int hbegp_predict_device(hbegp_model* model, long m, const void* xs_device, void
     if (!model) return fail(HBEGP_ERR_INVALID, "null model");
     if (!model->m->eng) return fail(HBEGP_ERR_INVALID, "the model's context has been destroyed");
     return model->m->predict_device(m, xs_device, mean_device, var_device, n_below_warn_device);
+}
+
+int hbegp_predict_mean_ei(hbegp_model* model, const hbegp_ynorm* yn, long m, const void* xs, double fmin, void* mean_out,
+                          void* ei_out, long* best_index, long* n_below_warn) {
+    if (!model) return fail(HBEGP_ERR_INVALID, "null model");
+    if (!model->m->eng) return fail(HBEGP_ERR_INVALID, "the model's context has been destroyed");
+    return model->m->predict_acquisition(0, yn, m, xs, fmin, mean_out, ei_out, best_index, n_below_warn);
+}
+
+int hbegp_predict_confidence_bound(hbegp_model* model, const hbegp_ynorm* yn, long m, const void* xs, double cb, void* out,
+                                   long* best_index, long* n_below_warn) {
+    if (!model) return fail(HBEGP_ERR_INVALID, "null model");
+    if (!model->m->eng) return fail(HBEGP_ERR_INVALID, "the model's context has been destroyed");
+    return model->m->predict_acquisition(1, yn, m, xs, cb, out, nullptr, best_index, n_below_warn);
 }
 
 int hbegp_minimize_by_gradient(hbegp_objective_fn objective, void* user, int n, double* x, const double* lo,

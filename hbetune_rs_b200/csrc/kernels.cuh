@@ -583,6 +583,115 @@ __global__ void k_var_finish(const T* __restrict__ part, int ld, int ntiles, lon
     var[row0 + r] = v;
 }
 
+template <typename T>
+__device__ __forceinline__ T mul_rn(T a, T b);
+template <>
+__device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
+template <>
+__device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
+template <typename T>
+__device__ __forceinline__ T add_rn(T a, T b);
+template <>
+__device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
+template <>
+__device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
+
+// Acquisition epilogues on the device.
+//   mode 0: predict_mean_ei_a (src/core/gpr.rs:179-212): out1 = de-normalised mean, out2 = EI in normalised
+//           units, EI evaluated in f64 from (mean, sqrt(var)) like acquisition.rs:141-171;
+//   mode 1: predict_confidence_bound (gpr.rs:94-112): out1 = location_from(mean + sqrt(var) * cb).
+// proj: 0 linear, 1 logarithmic (ynormalize.rs:215-225).
+template <typename T>
+__global__ void k_acquisition(const T* __restrict__ mean, const T* __restrict__ var, long m, int mode, int proj,
+                              T amplitude, T expected, double fmin_n, T cb, T* __restrict__ out1,
+                              T* __restrict__ out2) {
+    long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const T mu = mean[r], sd = dev_sqrt<T>(var[r]);
+    // un-fused multiply / add so that the result is bit-identical to the host-side YNorm<A>::location_from
+    auto location_from = [&](T y) -> T {
+        return proj == 0 ? add_rn<T>(mul_rn<T>(y - T(0.05), amplitude), expected)
+                         : add_rn<T>(dev_exp<T>(mul_rn<T>(y, amplitude)), expected);
+    };
+    if (mode == 0) {
+        const double mean_d = (double)mu, std_d = (double)sd;
+        double ei;
+        if (std_d <= 0.0 || fabs(std_d) < 4 * 2.2250738585072014e-308) {
+            ei = mean_d < fmin_n ? -(mean_d - fmin_n) : 0.0;
+        } else {
+            const double z = -(mean_d - fmin_n) / std_d;
+            const double cdf = 0.5 * erfc(-z * 0.70710678118654752440);
+            const double pdf = exp(-0.5 * z * z) * 0.39894228040143267794;
+            ei = -(mean_d - fmin_n) * cdf + std_d * pdf;
+        }
+        out1[r] = location_from(mu);
+        out2[r] = (T)ei;
+    } else {
+        out1[r] = location_from(add_rn<T>(mu, mul_rn<T>(sd, cb)));
+    }
+}
+
+// Arg-best over a vector in two deterministic stages.  want_max = 1: maximum, the LAST one wins ties
+// (Iterator::max_by, acquisition.rs:192-200); want_max = 0: minimum, the FIRST one wins (strict `<`,
+// minimize.rs:702-707).  NaNs never win.
+template <typename T>
+__global__ void __launch_bounds__(256) k_argbest_part(const T* __restrict__ v, long m, int want_max,
+                                                      T* __restrict__ pv, long* __restrict__ pi) {
+    __shared__ T sv[256];
+    __shared__ long si[256];
+    const long chunk = (m + gridDim.x - 1) / gridDim.x;
+    const long lo = (long)blockIdx.x * chunk, hi = min(m, lo + chunk);
+    T best = T(0);
+    long bi = -1;
+    for (long i = lo + threadIdx.x; i < hi; i += 256) {
+        const T x = v[i];
+        if (!(x == x)) continue;
+        if (bi < 0 || (want_max ? (x >= best) : (x < best))) {
+            best = x;
+            bi = i;
+        }
+    }
+    sv[threadIdx.x] = best;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const T a = sv[threadIdx.x], b = sv[threadIdx.x + o];
+            const long ia = si[threadIdx.x], ib = si[threadIdx.x + o];
+            bool take_b;
+            if (ib < 0) take_b = false;
+            else if (ia < 0) take_b = true;
+            else if (want_max) take_b = (b > a) || (b == a && ib > ia);
+            else take_b = (b < a) || (b == a && ib < ia);
+            if (take_b) {
+                sv[threadIdx.x] = b;
+                si[threadIdx.x] = ib;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        pv[blockIdx.x] = sv[0];
+        pi[blockIdx.x] = si[0];
+    }
+}
+
+template <typename T>
+__global__ void k_argbest_final(const T* __restrict__ pv, const long* __restrict__ pi, int nparts, int want_max,
+                                long* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    T best = T(0);
+    long bi = -1;
+    for (int p = 0; p < nparts; p++) {
+        if (pi[p] < 0) continue;
+        if (bi < 0 || (want_max ? (pv[p] >= best) : (pv[p] < best))) {
+            best = pv[p];
+            bi = pi[p];
+        }
+    }
+    *out = bi;
+}
+
 // out[i][j] = (i >= j) ? in[i][j] : in[j][i] for i, j < n  (hermitian fill of potri, lml.rs:62), packed n x n
 template <typename T>
 __global__ void k_sym_fill(const T* __restrict__ in, int np, int n, T* __restrict__ out, int mode) {

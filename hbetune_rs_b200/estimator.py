@@ -148,6 +148,29 @@ class SurrogateModelGPR:
         assert np.isfinite(ei).all(), "EI must be finite"
         return self.y_norm.project_location_from_normalized(mean), ei
 
+    def predict_mean_ei_device(self, x, fmin, want_best: bool = True):
+        """the whole of predict_mean_ei_a plus find_best_candidate_by_ei's argmax
+        (acquisition.rs:177-202, last maximum wins) in one device pass.  Returns (mean, ei, best_index)."""
+        x = np.ascontiguousarray(x, dtype=self.A)
+        m = x.shape[0]
+        mean, ei = np.empty(m, dtype=self.A), np.empty(m, dtype=self.A)
+        best, nb = C.c_long(-1), C.c_long(0)
+        check(lib.hbegp_predict_mean_ei(self.fitted.model._h, C.byref(self.y_norm._raw), m, _ptr(x), float(fmin), _ptr(mean),
+                                        _ptr(ei), C.byref(best) if want_best else None, C.byref(nb)), "hbegp_predict_mean_ei")
+        return mean, ei, best.value
+
+    def predict_confidence_bound_device(self, x, cb, want_best: bool = True):
+        """predict_confidence_bound for many points + find_best_individual_by_confidence_bound's argmin
+        (minimize.rs:680-714, first minimum wins).  Returns (bounds, best_index)."""
+        x = np.ascontiguousarray(x, dtype=self.A)
+        m = x.shape[0]
+        out = np.empty(m, dtype=self.A)
+        best, nb = C.c_long(-1), C.c_long(0)
+        check(lib.hbegp_predict_confidence_bound(self.fitted.model._h, C.byref(self.y_norm._raw), m, _ptr(x), float(cb), _ptr(out),
+                                                 C.byref(best) if want_best else None, C.byref(nb)),
+              "hbegp_predict_confidence_bound")
+        return out, best.value
+
     def predict_mean_ei(self, x, fmin):
         mean, ei = self.predict_mean_ei_a(np.asarray(x)[None, :], fmin)
         return mean[0], ei[0]

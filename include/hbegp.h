@@ -112,6 +112,21 @@ int hbegp_predict(hbegp_model* model, long m, const void* xs, void* mean, void* 
 int hbegp_predict_device(hbegp_model* model, long m, const void* xs_device, void* mean_device,
                          void* var_device, long* n_below_warn_device);
 
+/* ---- batched acquisition epilogues on the device (SURVEY section 8 "next" rows f1 / f2) ------------- */
+/* Forward declaration of the y-normalisation record defined below. */
+struct hbegp_ynorm;
+/* predict_mean_ei_a (src/core/gpr.rs:179-212) for m candidates in one call: mean_out[m] = de-normalised mean,
+ * ei_out[m] = expected improvement (acquisition.rs:141-171, evaluated in f64) against fmin given in NATURAL
+ * units (it is projected into normalised space in A first, gpr.rs:192-196).  best_index (may be NULL) receives
+ * find_best_candidate_by_ei's argmax (acquisition.rs:177-202: the LAST maximum wins).  Any output may be NULL. */
+int hbegp_predict_mean_ei(hbegp_model* model, const struct hbegp_ynorm* yn, long m, const void* xs, double fmin,
+                          void* mean_out, void* ei_out, long* best_index, long* n_below_warn);
+/* predict_confidence_bound (src/core/gpr.rs:94-112) for m points: out[m] = location_from(mean + sqrt(var) * cb);
+ * best_index (may be NULL) = find_best_individual_by_confidence_bound's argmin (minimize.rs:680-714: strict `<`,
+ * the FIRST minimum wins). */
+int hbegp_predict_confidence_bound(hbegp_model* model, const struct hbegp_ynorm* yn, long m, const void* xs,
+                                   double cb, void* out, long* best_index, long* n_below_warn);
+
 /* ---- host-side pieces of the reference interface (no GPU needed) -------------------------------- */
 /* Bounded L-BFGS used by hbegp_fit_runs, exposed with a callback objective
  * (objective(x, grad_out, user) -> f), mirroring minimize_by_gradient (src/util/gradmin.rs:35-60).
