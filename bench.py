@@ -65,6 +65,19 @@ def workload(args):
     return A, x, y, lo, hi, thetas, xs
 
 
+def base_config(args, B):
+    return {"workload": f"ns_fit_n{args.n}_d{args.d}_B{B}", "n": args.n, "d": args.d, "restarts": args.restarts, "B": B,
+            "m": args.m}
+
+
+def ncu_traffic():
+    """DRAM bytes per launch from the committed `ncu --set full` captures (profiles/r01_ncu_traffic.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+    except (OSError, ValueError):
+        return {}
+
+
 class ClockSampler:
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -146,8 +159,7 @@ def run_reference(args):
         "impl": "reference", "metric": "gp_fit_lml_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"ns_fit_n{args.n}_d{args.d}_B{len(thetas)}", "n": args.n, "d": args.d,
-                   "restarts": args.restarts},
+        "config": base_config(args, len(thetas)),
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -326,9 +338,9 @@ def main():
             "metric": "gp_fit_lml_evals_per_s", "value": evals_per_s, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"ns_fit_n{n}_d{d}_B{B}", "n": n, "d": d, "restarts": args.restarts, "B": B, "m": m,
-                       "sharding": f"restarts and candidate rows over {world} rank(s); one n x n factorisation per GPU",
-                       "l2": f"per-step working set {B // world * 2 * n * n * x.itemsize / 1e9:.1f} GB per GPU >> 126 MB L2"},
+            "config": dict(base_config(args, B),
+                           sharding=f"restarts and candidate rows over {world} rank(s); one n x n factorisation per GPU",
+                           l2=f"inputs larger than L2: per-step working set {B // world * 2 * n * n * x.itemsize / 1e9:.1f} GB per GPU vs 126 MB"),
             "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "evals/s",
                     "h2d_bytes_per_step": int(x.nbytes + y.nbytes + thetas.nbytes),
                     "d2h_bytes_per_step": int(B * (p + 1) * 8 + B * 4)},
@@ -351,11 +363,22 @@ def main():
             "algorithmic": "2 n^3 / 3 FLOP per evaluation (Cholesky factor n^3/3 + its triangular inverse n^3/3)",
         }
         out["phases"] = phases
+        traffic = ncu_traffic()
+        t_dense = (phases["factor_inverse_ms"] + phases["alpha_kinv_ms"]) * 1e-3
+        tf_dense = 1.0 * n ** 3 * nb / t_dense * 1e-12
         out["cholesky_fp64_tflops"] = tf_fi
         out["lml_eval_fp64_tflops"] = tf_eval
         out["predict_var_fp64_tflops"] = tf_var
         out["rooflines"] = {
             "lml_eval_n3": {"achieved": tf_eval, "peak": peak_tf, "frac": tf_eval / peak_tf, "unit": "TFLOP/s"},
+            "dense_phases_n3": {"achieved": tf_dense, "peak": peak_tf, "frac": tf_dense / peak_tf, "unit": "TFLOP/s",
+                                "what": "all gemm_kernel + k_leaf launches (factor, inverse, K^-1 = W^T W): n^3 FLOP per evaluation"},
+            "kinv_gemm": dict({"bound": "tensor", "unit": "TFLOP/s", "peak": peak_tf,
+                               "algorithmic": "n^3/3 FLOP, 8 n^2 bytes (read W lower, write K^-1 lower) per matrix"},
+                              **traffic.get("kinv_gemm", {})),
+            "predict_var_gemm": dict({"bound": "tensor", "unit": "TFLOP/s", "peak": peak_tf,
+                                      "algorithmic": "m n^2 FLOP per chunk of m candidates"},
+                                     **traffic.get("predict_var_gemm", {})),
             "predict_var_mn2": {"achieved": tf_var * world, "peak": peak_tf * world, "frac": tf_var / peak_tf, "unit": "TFLOP/s"},
             "assemble_hbm": {"achieved": nb * (8.0 * n * d + x.itemsize * n * (n + 1) / 2) / (phases["assemble_ms"] * 1e-3) * 1e-9,
                              "peak": peaks().get("hbm_gbs"), "unit": "GB/s"},

@@ -180,6 +180,9 @@ __global__ void __launch_bounds__(GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR,
     }
 
     const int lr = lane >> 2, lc = lane & 3;
+    // warp-tile-relative row of accumulator slot i / column of slot j (see the two micro-kernels below)
+    auto row_of = [&](int i) { return (F64 || A_KMAJOR) ? i * 8 + lr : 4 * lr + i; };
+    auto col_of = [&](int j) { return F64 ? j * 8 + 2 * lc : (B_KMAJOR ? j * 4 + lc : 8 * lc + j); };
     for (int kt = 0; kt < nk; kt++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -208,23 +211,49 @@ __global__ void __launch_bounds__(GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR,
                     for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
         } else {
+            // FP32 (FFMA): 4 x 8 outputs per thread, operands fetched four k at a time with 16-byte shared loads
+            // (12 LDS.128 per 128 FFMA).  Thread-to-row/column mapping follows the contiguous direction of the
+            // staged tile: k-major tiles give rows lr + 8 i / columns lc + 4 j, row-major tiles give the
+            // contiguous groups 4 lr + i / 8 lc + j.
+            static_assert(F64 || (FM == 4 && FN == 8), "f32 micro-kernel is written for 32x32 warp tiles");
 #pragma unroll
-            for (int k = 0; k < BK; k++) {
-                T a[FM], b[FN];
+            for (int k4 = 0; k4 < BK; k4 += 4) {
+                float av[4][4], bv[8][4];
+                if (A_KMAJOR) {
 #pragma unroll
-                for (int i = 0; i < FM; i++) {
-                    int row = wm * WM + i * 8 + lr;
-                    a[i] = A_KMAJOR ? sA[row * Cfg::A_STRIDE + k] : sA[k * Cfg::A_STRIDE + row];
+                    for (int i = 0; i < 4; i++) {
+                        const float4 t = *reinterpret_cast<const float4*>(&sA[(wm * WM + i * 8 + lr) * Cfg::A_STRIDE + k4]);
+                        av[i][0] = t.x; av[i][1] = t.y; av[i][2] = t.z; av[i][3] = t.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                        const float4 t = *reinterpret_cast<const float4*>(&sA[(k4 + kk) * Cfg::A_STRIDE + wm * WM + 4 * lr]);
+                        av[0][kk] = t.x; av[1][kk] = t.y; av[2][kk] = t.z; av[3][kk] = t.w;
+                    }
+                }
+                if (B_KMAJOR) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 t = *reinterpret_cast<const float4*>(&sB[(wn * WN + j * 4 + lc) * Cfg::B_STRIDE + k4]);
+                        bv[j][0] = t.x; bv[j][1] = t.y; bv[j][2] = t.z; bv[j][3] = t.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                        const float4 t0 = *reinterpret_cast<const float4*>(&sB[(k4 + kk) * Cfg::B_STRIDE + wn * WN + 8 * lc]);
+                        const float4 t1 = *reinterpret_cast<const float4*>(&sB[(k4 + kk) * Cfg::B_STRIDE + wn * WN + 8 * lc + 4]);
+                        bv[0][kk] = t0.x; bv[1][kk] = t0.y; bv[2][kk] = t0.z; bv[3][kk] = t0.w;
+                        bv[4][kk] = t1.x; bv[5][kk] = t1.y; bv[6][kk] = t1.z; bv[7][kk] = t1.w;
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < FN; j++) {
-                    int col = wn * WN + j * 4 + lc;
-                    b[j] = B_KMAJOR ? sB[col * Cfg::B_STRIDE + k] : sB[k * Cfg::B_STRIDE + col];
-                }
+                for (int kk = 0; kk < 4; kk++)
 #pragma unroll
-                for (int i = 0; i < FM; i++)
+                    for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int j = 0; j < FN; j++) acc[i][j][0] = fmaf(a[i], b[j], acc[i][j][0]);
+                        for (int j = 0; j < 8; j++)
+                            acc[i % FM][j % FN][0] = fmaf(av[i][kk], bv[j][kk], acc[i % FM][j % FN][0]);
             }
         }
     }
@@ -243,7 +272,7 @@ __global__ void __launch_bounds__(GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR,
                 for (int e = 0; e < ACC; e++) s += acc[i][j][e] * acc[i][j][e];
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (lc == 0) red[(wm * WM + i * 8 + lr) * Cfg::WARPS_N + wn] = s;
+            if (lc == 0) red[(wm * WM + row_of(i)) * Cfg::WARPS_N + wn] = s;
         }
         __syncthreads();
         T* out = p.rowsumsq + (long)blockIdx.z * p.s_rs;
@@ -260,11 +289,11 @@ __global__ void __launch_bounds__(GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR,
     const bool use_beta = (p.beta != T(0));
 #pragma unroll
     for (int i = 0; i < FM; i++) {
-        const long row = m0 + wm * WM + i * 8 + lr;
+        const long row = m0 + wm * WM + row_of(i);
 #pragma unroll
         for (int j = 0; j < FN; j++) {
             if constexpr (F64) {
-                const int col = n0 + wn * WN + j * 8 + 2 * lc;
+                const int col = n0 + wn * WN + col_of(j);
                 double2* ptr = reinterpret_cast<double2*>(gC + row * p.ldc + col);
                 double2 v;
                 v.x = p.alpha * acc[i][j][0];
@@ -276,7 +305,7 @@ __global__ void __launch_bounds__(GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR,
                 }
                 *ptr = v;
             } else {
-                const int col = n0 + wn * WN + j * 4 + lc;
+                const int col = n0 + wn * WN + col_of(j);
                 T* ptr = gC + row * p.ldc + col;
                 T v = p.alpha * acc[i][j][0];
                 if (use_beta) v += p.beta * (*ptr);
@@ -314,9 +343,13 @@ inline int pick_gemm_tile(int M, int N) {
     return (gemm_tile_pref() == 128 && M % 128 == 0 && N % 128 == 0) ? 128 : 64;
 }
 
+// warp-tile height of the optional 128x128 configuration: 64x32 DMMA warp tiles for f64, 32x32 FFMA for f32
+template <typename T>
+constexpr int wm128() { return std::is_same<T, double>::value ? 64 : 32; }
+
 template <typename T, bool AK, bool BK_>
 inline cudaError_t launch_gemm(const GemmArgs<T>& a, int batch, cudaStream_t stream) {
-    if (pick_gemm_tile(a.M, a.N) == 128) return launch_gemm_cfg<T, 128, 128, 64, 32, AK, BK_>(a, batch, stream);
+    if (pick_gemm_tile(a.M, a.N) == 128) return launch_gemm_cfg<T, 128, 128, wm128<T>(), 32, AK, BK_>(a, batch, stream);
     return launch_gemm_cfg<T, 64, 64, 32, 32, AK, BK_>(a, batch, stream);
 }
 

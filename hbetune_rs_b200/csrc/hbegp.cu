@@ -757,9 +757,9 @@ static int configure_gemms() {
 #define HBEGP_CFG(BM, BN, WM, WN, AK, BK_)                                                                        \
     CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<T, BM, BN, WM, WN, AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)GemmCfg<T, BM, BN, WM, WN, AK, BK_>::SMEM_BYTES))
-    HBEGP_CFG(128, 128, 64, 32, true, true);
-    HBEGP_CFG(128, 128, 64, 32, true, false);
-    HBEGP_CFG(128, 128, 64, 32, false, false);
+    HBEGP_CFG(128, 128, wm128<T>(), 32, true, true);
+    HBEGP_CFG(128, 128, wm128<T>(), 32, true, false);
+    HBEGP_CFG(128, 128, wm128<T>(), 32, false, false);
     HBEGP_CFG(64, 64, 32, 32, true, true);
     HBEGP_CFG(64, 64, 32, 32, true, false);
     HBEGP_CFG(64, 64, 32, 32, false, false);
