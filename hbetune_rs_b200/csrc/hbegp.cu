@@ -46,6 +46,9 @@ static int fail(int code, const std::string& msg) {
 
 static inline int round_up(long v, int m) { return (int)(((v + m - 1) / m) * m); }
 
+// dynamic shared memory the d-dependent kernels may use (opt-in limit on sm_100a is 227 KB)
+constexpr size_t kMaxFeatureSmem = 200 * 1024;
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -169,6 +172,8 @@ struct Engine : EngineBase {
     int set_data(long n_, int d_, const void* x, const void* y, bool on_device) override {
         if (n_ <= 0 || d_ <= 0 || !x || !y) return fail(HBEGP_ERR_INVALID, "set_data: n, d must be positive and x, y non-null");
         if (n_ > 46000) return fail(HBEGP_ERR_INVALID, "set_data: n too large for a single-GPU factorisation");
+        if ((2 * (size_t)d_ * TILE + 2 * TILE) * sizeof(T) + 8 * (size_t)(d_ + 2) * sizeof(double) > kMaxFeatureSmem)
+            return fail(HBEGP_ERR_UNSUPPORTED, "set_data: too many features for the shared-memory tiles of the assembly kernels");
         CUDA_TRY(cudaSetDevice(device));
         const void *oldx = dX.p, *oldy = dY.p;
         const bool same_shape = (n == n_ && d == d_);
@@ -414,8 +419,12 @@ struct Engine : EngineBase {
 
     // Evaluates `cnt` <= cap parameter sets already staged in h_prm; results land in h_out / h_status.
     int run_chunk(int nu2, int cnt, bool want_grad, bool want_kinv) {
+        // Graphs pay off where the launch sequence is latency bound (small n).  At n > 2048 kernels run for
+        // hundreds of microseconds, the asynchronous launches are hidden anyway, and re-instantiating a
+        // ~1000-node graph for every distinct batch size of a fit costs more than it saves (measured: 10.2 s
+        // with graphs vs 9.5 s without for the north-star fit; 0.37 s vs 0.39 s at n = 1024).
         const bool legacy = (stream == nullptr || stream == cudaStreamLegacy);
-        if (!use_graphs || legacy) {
+        if (!use_graphs || legacy || np > 2048) {
             int rc = issue_chunk(nu2, cnt, want_grad, want_kinv);
             if (rc) return rc;
             CUDA_TRY(cudaStreamSynchronize(stream));
@@ -560,13 +569,6 @@ struct ModelT : Model {
         Engine<T>* e = static_cast<Engine<T>*>(eng);
         cudaStream_t st = e->stream;
         const size_t ksm = (2 * (size_t)d * TILE + TILE) * sizeof(T);
-        if (ksm > 48 * 1024) {
-            static bool done = false;
-            if (!done) {
-                CUDA_TRY(cudaFuncSetAttribute(k_kstar_mean<T, NU2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksm));
-                done = true;
-            }
-        }
         if (var == nullptr) {
             long rows = round_up(m, TILE);
             k_kstar_mean<T, NU2><<<(unsigned)(rows / TILE), 256, ksm, st>>>(xs, m, 0, d, (const T*)xsT.p, (int)n, np, (const T*)ls.p,
@@ -764,6 +766,17 @@ static int configure_gemms() {
     HBEGP_CFG(64, 64, 32, 32, true, false);
     HBEGP_CFG(64, 64, 32, 32, false, false);
 #undef HBEGP_CFG
+    // kernels whose dynamic shared memory grows with the feature count d (two d x 64 operand tiles)
+    const int big = (int)kMaxFeatureSmem;
+    CUDA_TRY(cudaFuncSetAttribute(k_assemble<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(k_assemble<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(k_assemble<T, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(k_grad_contract<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(k_grad_contract<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(k_grad_contract<T, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(k_kstar_mean<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(k_kstar_mean<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(k_kstar_mean<T, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     return HBEGP_OK;
 }
 
@@ -794,12 +807,14 @@ static int fit_runs_impl(EngineBase* e, double nu, int n_runs, const double* sta
     std::vector<int> live;
     std::vector<double> th, lml, grad;
     std::vector<int> st;
+    const bool trace = getenv("HBEGP_TRACE") != nullptr;  // per-round batch sizes on stderr
     for (;;) {
         live.clear();
         for (int r = 0; r < n_runs; r++)
             if (!opt[r].done()) live.push_back(r);
         if (live.empty()) break;
         const int B = (int)live.size();
+        if (trace) fprintf(stderr, "hbegp fit round: %d live runs\n", B);
         th.resize((size_t)B * p);
         lml.resize(B);
         grad.resize((size_t)B * p);

@@ -48,27 +48,21 @@ int main() {
     CK(cudaMemcpy(A, h.data(), bytes, cudaMemcpyHostToDevice)); CK(cudaMemcpy(B, h.data(), bytes, cudaMemcpyHostToDevice));
     struct Shape { int M, N, K, b, kmode, lower; };
     Shape shapes[] = {{2048, 2048, 2048, 4, K_FULL, 0}, {4096, 4096, 4096, 1, K_FULL, 0}, {2048, 2048, 2048, 4, K_LE_N, 0},
-                      {1024, 1024, 1024, 16, K_FULL, 0}, {512, 512, 512, 16, K_FULL, 0}, {2048, 2048, 2048, 4, K_FULL, 1}};
+                      {1536, 1536, 1536, 8, K_FULL, 0}};
     for (auto s : shapes) {
         printf("---- shape M=%d N=%d K=%d batch=%d kmode=%d lower=%d\n", s.M, s.N, s.K, s.b, s.kmode, s.lower);
 #define RUN(BM, BN, WM, WN, BKK, STG) run<BM, BN, WM, WN, true, true, BKK, STG>(#BM "x" #BN " w" #WM "x" #WN " bk" #BKK " s" #STG, s.M, s.N, s.K, s.b, s.kmode, s.lower, A, B, C)
-        RUN(128, 128, 64, 32, 16, 3);
-        RUN(128, 128, 64, 32, 16, 4);
-        RUN(128, 128, 64, 32, 32, 2);
-        RUN(128, 128, 64, 32, 32, 3);
-        RUN(128, 128, 32, 64, 16, 3);
-        RUN(128, 128, 32, 32, 16, 3);
-        RUN(128, 128, 32, 32, 16, 4);
-        RUN(128, 128, 32, 32, 32, 3);
-        RUN(128, 64, 32, 32, 16, 3);
-        RUN(128, 64, 32, 32, 16, 4);
-        RUN(128, 64, 64, 32, 16, 3);
-        RUN(64, 128, 32, 32, 16, 3);
         RUN(64, 64, 32, 32, 16, 3);
-        RUN(64, 64, 32, 32, 16, 4);
-        RUN(64, 64, 32, 32, 32, 3);
-        RUN(256, 128, 64, 32, 16, 3);
-        RUN(256, 64, 64, 32, 16, 3);
+        RUN(64, 64, 32, 32, 32, 2);
+        RUN(64, 64, 32, 32, 8, 4);
+        RUN(64, 64, 32, 32, 8, 6);
+        RUN(64, 64, 32, 64, 16, 3);
+        RUN(64, 64, 64, 32, 16, 3);
+        RUN(64, 128, 32, 64, 16, 3);
+        RUN(128, 64, 64, 32, 16, 3);
+        RUN(128, 64, 64, 32, 32, 2);
+        RUN(128, 128, 64, 64, 16, 3);
+        RUN(96, 96, 48, 48, 16, 3);
     }
     // TN layout check on one shape (A m-major, B n-major)
     printf("---- layouts (128x128 w64x32)\n");

@@ -40,7 +40,7 @@ def test_factor_intermediates_f64(n, d):
 
 
 @pytest.mark.parametrize("A", [np.float64, np.float32])
-@pytest.mark.parametrize("n,d,B", [(50, 2, 3), (150, 4, 5), (300, 8, 4)])
+@pytest.mark.parametrize("n,d,B", [(50, 2, 3), (150, 4, 5), (300, 8, 4), (90, 64, 2)])
 def test_lml_and_gradient_batch(A, n, d, B):
     x, y = synth(n, d, A=A)
     thetas = random_thetas(B, d, seed=7 + n, noise=(1e-2, 1.0) if A == np.float64 else (1e-1, 1.0))
@@ -80,6 +80,9 @@ def test_unsupported_nu_and_errors():
     x, y = synth(10, 2)
     with _ctx(np.float64) as ctx:
         with pytest.raises(h.HbegpError) as e:
+            ctx.set_data(np.zeros((4, 400)), np.zeros(4))  # feature tiles would not fit shared memory
+        assert e.value.code == -4
+        with pytest.raises(h.HbegpError) as e:
             ctx.lml_grad_batch(random_thetas(1, 0))  # no data yet
         ctx.set_data(x, y)
         with pytest.raises(h.HbegpError) as e:
@@ -118,7 +121,7 @@ def test_theta_clamping_matches_with_clamped_theta():
 
 
 @pytest.mark.parametrize("A", [np.float64, np.float32])
-@pytest.mark.parametrize("n,d,m", [(5, 1, 1), (120, 3, 300), (257, 6, 1000), (64, 2, 64)])
+@pytest.mark.parametrize("n,d,m", [(5, 1, 1), (120, 3, 300), (257, 6, 1000), (64, 2, 64), (70, 50, 130)])
 def test_predict_mean_and_variance(A, n, d, m):
     x, y = synth(n, d, A=A)
     xs = np.random.default_rng(2).random((m, d)).astype(A)
