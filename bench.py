@@ -183,6 +183,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout to the single JSON line: NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION/INFO
+        os.environ["NCCL_DEBUG"] = os.environ.get("HBEGP_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
