@@ -183,8 +183,13 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the single JSON line: NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION/INFO
-        os.environ["NCCL_DEBUG"] = os.environ.get("HBEGP_NCCL_DEBUG", "WARN")
+        # keep stdout to the single JSON line: at NCCL_DEBUG=WARN / VERSION / INFO NCCL prints its version banner
+        # on stdout; unset means no banner, and anything it does log goes to stderr
+        if "HBEGP_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["HBEGP_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():

@@ -99,10 +99,10 @@ struct Model {
     int d = 0, np = 0, nu2 = 5;
     double c = 1.0;
     DevBuf W, alpha, xsT, ls;  // inverse Cholesky factor (np x np), alpha (np), scaled X^T (d x np), length scales
-    DevBuf kstar, part, nbelow, xs_tmp, mean_tmp, var_tmp;
+    DevBuf kstar, part, pmean, nbelow, xs_tmp, mean_tmp, var_tmp;
     void release_all() {
         W.release(); alpha.release(); xsT.release(); ls.release();
-        kstar.release(); part.release(); nbelow.release(); xs_tmp.release(); mean_tmp.release(); var_tmp.release();
+        kstar.release(); part.release(); pmean.release(); nbelow.release(); xs_tmp.release(); mean_tmp.release(); var_tmp.release();
         acq1.release(); acq2.release(); argv.release(); argi.release();
     }
     virtual ~Model() {
@@ -564,29 +564,81 @@ struct ModelT : Model {
         return (int)std::min<long>(rows, 1 << 16);
     }
 
+    // m <= 64: latency path (see k_kstar_small)
+    template <int NU2>
+    int predict_small(int m, const T* xs, T* mean, T* var, unsigned long long* nb) {
+        Engine<T>* e = static_cast<Engine<T>*>(eng);
+        cudaStream_t st = e->stream;
+        const int ntiles = np / TILE, nctas = np / 8;
+        int rc;
+        if ((rc = part.ensure(((size_t)ntiles + nctas) * 64 * sizeof(T)))) return rc;
+        if (var && (rc = kstar.ensure((size_t)64 * np * sizeof(T)))) return rc;
+        T* pmean = (T*)part.p;
+        T* psq = pmean + (size_t)ntiles * 64;
+        const size_t sm = ((size_t)m * d + 8 * 16) * sizeof(T);
+        k_kstar_small<T, NU2><<<ntiles, 256, sm, st>>>(xs, m, d, (const T*)xsT.p, (int)n, np, (const T*)ls.p, (T)c, (const T*)alpha.p,
+                                                      var ? (T*)kstar.p : nullptr, pmean);
+        e->launches++;
+        if (var) {
+            k_wmatvec_small<T><<<dim3(nctas, (m + 15) / 16), 256, 0, st>>>((const T*)W.p, np, (const T*)kstar.p, m, psq);
+            e->launches++;
+        }
+        k_small_finish<T><<<1, 64, 0, st>>>(pmean, ntiles, psq, nctas, m, (T)c, mean, var, nb);
+        e->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return HBEGP_OK;
+    }
+
     template <int NU2>
     int predict_impl(long m, const T* xs, T* mean, T* var, unsigned long long* nb) {
         Engine<T>* e = static_cast<Engine<T>*>(eng);
         cudaStream_t st = e->stream;
+        if (m <= 64 && (size_t)m * d * sizeof(T) <= 40 * 1024) return predict_small<NU2>((int)m, xs, mean, var, nb);
         const size_t ksm = (2 * (size_t)d * TILE + TILE) * sizeof(T);
+        const int ttiles = np / TILE;
+        // split the train tiles over grid.y when the candidate tiles alone would leave most SMs idle
+        auto col_split = [&](int row_tiles) {
+            int s = (3 * 148 + row_tiles - 1) / row_tiles;
+            return std::max(1, std::min(s, ttiles));
+        };
+        int rc;
         if (var == nullptr) {
-            long rows = round_up(m, TILE);
-            k_kstar_mean<T, NU2><<<(unsigned)(rows / TILE), 256, ksm, st>>>(xs, m, 0, d, (const T*)xsT.p, (int)n, np, (const T*)ls.p,
-                                                                           (T)c, (const T*)alpha.p, nullptr, mean);
-            e->launches++;
+            const int chunk_cap = 1 << 20;
+            for (long row0 = 0; row0 < m; row0 += chunk_cap) {
+                const int rows = round_up(std::min<long>(chunk_cap, m - row0), TILE);
+                const int S = col_split(rows / TILE), tpc = (ttiles + S - 1) / S, ns = (ttiles + tpc - 1) / tpc;
+                T* pm = nullptr;
+                if (ns > 1) {
+                    if ((rc = pmean.ensure((size_t)ns * rows * sizeof(T)))) return rc;
+                    pm = (T*)pmean.p;
+                }
+                k_kstar_mean<T, NU2><<<dim3((unsigned)(rows / TILE), ns), 256, ksm, st>>>(xs, m, row0, d, (const T*)xsT.p, (int)n, np,
+                                                                                       (const T*)ls.p, (T)c, (const T*)alpha.p, nullptr,
+                                                                                       mean, tpc, pm, rows);
+                e->launches++;
+                if (pm) {
+                    k_var_finish<T><<<(rows + 255) / 256, 256, 0, st>>>(nullptr, 0, 0, rows, m, row0, (T)c, nullptr, nb, pm, ns, rows, mean);
+                    e->launches++;
+                }
+            }
             CUDA_TRY(cudaGetLastError());
             return HBEGP_OK;
         }
         const int chunk = (int)std::min<long>(predict_chunk_rows(), round_up(m, 128));
         const int bn = pick_gemm_tile(128, np);  // rows are always a multiple of 128
         const int ntile = np / bn;
-        int rc;
         if ((rc = kstar.ensure((size_t)chunk * np * sizeof(T)))) return rc;
         if ((rc = part.ensure((size_t)chunk * ntile * sizeof(T)))) return rc;
         for (long row0 = 0; row0 < m; row0 += chunk) {
             const int rows = (int)std::min<long>(chunk, round_up(m - row0, 128));
-            k_kstar_mean<T, NU2><<<rows / TILE, 256, ksm, st>>>(xs, m, row0, d, (const T*)xsT.p, (int)n, np, (const T*)ls.p, (T)c,
-                                                               (const T*)alpha.p, (T*)kstar.p, mean);
+            const int S = col_split(rows / TILE), tpc = (ttiles + S - 1) / S, ns = (ttiles + tpc - 1) / tpc;
+            T* pm = nullptr;
+            if (ns > 1) {
+                if ((rc = pmean.ensure((size_t)ns * rows * sizeof(T)))) return rc;
+                pm = (T*)pmean.p;
+            }
+            k_kstar_mean<T, NU2><<<dim3(rows / TILE, ns), 256, ksm, st>>>(xs, m, row0, d, (const T*)xsT.p, (int)n, np, (const T*)ls.p, (T)c,
+                                                                       (const T*)alpha.p, (T*)kstar.p, mean, tpc, pm, rows);
             e->launches++;
             // |W k*|^2 per candidate: U = k* W^T restricted to k <= column tile, squared and row-summed in the epilogue
             GemmArgs<T> g{};
@@ -600,7 +652,7 @@ struct ModelT : Model {
             g.raster_group = (int)std::max<size_t>(1, ((size_t)48 << 20) / ((size_t)bn * np * sizeof(T)));
             CUDA_TRY((launch_gemm<T, true, true>(g, 1, st)));
             e->launches++;
-            k_var_finish<T><<<(rows + 255) / 256, 256, 0, st>>>((const T*)part.p, ntile, ntile, rows, m, row0, (T)c, var, nb);
+            k_var_finish<T><<<(rows + 255) / 256, 256, 0, st>>>((const T*)part.p, ntile, ntile, rows, m, row0, (T)c, var, nb, pm, ns, rows, mean);
             e->launches++;
             CUDA_TRY(cudaGetLastError());
         }

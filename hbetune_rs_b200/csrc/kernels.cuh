@@ -507,7 +507,10 @@ template <typename T, int NU2>
 __global__ void __launch_bounds__(256) k_kstar_mean(const T* __restrict__ xs, long m, long row0, int d,
                                                     const T* __restrict__ xsT_train, int n, int np,
                                                     const T* __restrict__ ls, T c, const T* __restrict__ alpha,
-                                                    T* __restrict__ kstar, T* __restrict__ mean) {
+                                                    T* __restrict__ kstar, T* __restrict__ mean, int tiles_per_cta,
+                                                    T* __restrict__ pmean, long pm_stride) {
+    // grid.y splits the train tiles when there are too few candidate tiles to fill the GPU; the partial means of
+    // split y go to pmean[y * pm_stride + chunk_row] and are summed in order by k_var_finish.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* xc = reinterpret_cast<T*>(smem_raw);  // [d][64] candidates (scaled)
     T* xt = xc + d * TILE;                   // [d][64] train tile
@@ -520,7 +523,8 @@ __global__ void __launch_bounds__(256) k_kstar_mean(const T* __restrict__ xs, lo
         xc[k * TILE + r] = (gr < m) ? xs[gr * d + k] / ls[k] : T(0);
     }
     T macc[4] = {T(0), T(0), T(0), T(0)};
-    for (int j0 = 0; j0 < np; j0 += TILE) {
+    const int jbeg = blockIdx.y * tiles_per_cta * TILE, jend = min(np, jbeg + tiles_per_cta * TILE);
+    for (int j0 = jbeg; j0 < jend; j0 += TILE) {
         __syncthreads();
         for (int e = tid; e < d * TILE; e += 256) {
             int k = e / TILE, r = e % TILE;
@@ -563,17 +567,125 @@ __global__ void __launch_bounds__(256) k_kstar_mean(const T* __restrict__ xs, lo
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         long gr = row0 + r0 + ty + 16 * a;
-        if (tx == 0 && gr < m) mean[gr] = v;
+        if (tx == 0) {
+            if (pmean != nullptr) pmean[(long)blockIdx.y * pm_stride + r0 + ty + 16 * a] = v;
+            else if (gr < m) mean[gr] = v;
+        }
     }
+}
+
+// ---- small-batch prediction (m <= 64 candidates; the reference's callers predict ONE point per call,
+// SURVEY F4).  The throughput path above loops one CTA over all train tiles per 64 candidates and pads the
+// variance GEMM to 128 rows, which is latency bound for a handful of points (n = 4096, m = 1: 0.62 ms).  Here the
+// parallelism comes from the train dimension instead: k* per train tile, then one warp per row of W = L^-1.
+
+// k*[r][j] for train tile blockIdx.x and all m candidates; pmean[tile][r] = sum_{j in tile} k*[r][j] alpha[j].
+template <typename T, int NU2>
+__global__ void __launch_bounds__(256) k_kstar_small(const T* __restrict__ xs, int m, int d,
+                                                     const T* __restrict__ xsT_train, int n, int np,
+                                                     const T* __restrict__ ls, T c, const T* __restrict__ alpha,
+                                                     T* __restrict__ kstar, T* __restrict__ pmean) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* xc = reinterpret_cast<T*>(smem_raw);  // [m][d] scaled candidates
+    T* red = xc + (size_t)m * d;             // [8 warps][16 slots]
+    const int tid = threadIdx.x, j = blockIdx.x * TILE + (tid & 63), g = tid >> 6, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < m * d; e += 256) xc[e] = xs[e] / ls[e % d];
+    __syncthreads();
+    const T aj = alpha[j];
+    for (int q = 0; q < 16; q++) {
+        const int r = g + 4 * q;  // warp-uniform
+        T contrib = T(0);
+        if (r < m) {
+            T acc = T(0);
+            for (int k = 0; k < d; k++) {
+                const T df = xc[r * d + k] - xsT_train[(long)k * np + j];
+                acc += df * df;
+            }
+            const T v = (j < n) ? c * matern_corr<T, NU2>(dev_sqrt<T>(acc)) : T(0);
+            if (kstar != nullptr) kstar[(long)r * np + j] = v;
+            contrib = v * aj;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        if (lane == 0) red[warp * 16 + q] = contrib;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        const int r = tid;  // candidate r = g + 4 q was reduced by warps 2g and 2g + 1
+        if (r < m) {
+            const int gg = r & 3, q = r >> 2;
+            pmean[(long)blockIdx.x * 64 + r] = red[(2 * gg) * 16 + q] + red[(2 * gg + 1) * 16 + q];
+        }
+    }
+}
+
+// One warp per row i of W: u_i[r] = sum_{k <= i} W[i][k] k*[r][k] for the 16 candidates of group blockIdx.y;
+// psq[cta][r] = sum over the CTA's 8 rows of u_i[r]^2 (the predictive variance is c + 1e-5 - |W k*|^2).
+template <typename T>
+__global__ void __launch_bounds__(256) k_wmatvec_small(const T* __restrict__ W, int np, const T* __restrict__ kstar, int m,
+                                                       T* __restrict__ psq) {
+    __shared__ T red[8][16];
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * 16;
+    const T* wr = W + (long)row * np;
+    T acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) acc[q] = T(0);
+    for (int k = lane; k <= row; k += 32) {
+        const T wv = wr[k];
+#pragma unroll
+        for (int q = 0; q < 16; q++)
+            if (r0 + q < m) acc[q] = fma(wv, kstar[(long)(r0 + q) * np + k], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        T v = acc[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][q] = v * v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16 && r0 + threadIdx.x < m) {
+        T s = T(0);
+#pragma unroll
+        for (int w = 0; w < 8; w++) s += red[w][threadIdx.x];
+        psq[(long)blockIdx.x * 64 + r0 + threadIdx.x] = s;
+    }
+}
+
+// mean[r] = sum_tiles pmean[tile][r]; var[r] = c + 1e-5 - sum_ctas psq[cta][r] (counted / clamped like k_var_finish)
+template <typename T>
+__global__ void k_small_finish(const T* __restrict__ pmean, int ntiles, const T* __restrict__ psq, int nctas, int m, T c,
+                               T* __restrict__ mean, T* __restrict__ var, unsigned long long* __restrict__ n_below) {
+    const int r = threadIdx.x;
+    if (r >= m) return;
+    T s = T(0);
+    for (int t = 0; t < ntiles; t++) s += pmean[(long)t * 64 + r];
+    mean[r] = s;
+    if (var == nullptr) return;
+    T q = T(0);
+    for (int t = 0; t < nctas; t++) q += psq[(long)t * 64 + r];
+    const T min_noise = T(1e-5);
+    T v = c + min_noise - q;
+    if (v < -dev_sqrt<T>(min_noise)) atomicAdd(n_below, 1ULL);
+    if (v < T(0)) v = T(0);
+    var[r] = v;
 }
 
 // var[r] = c + 1e-5 - sum_t part[r][t]; counts values < -sqrt(1e-5) then clamps at 0
 // (src/gpr/predict.rs:25-48, :104-127).
 template <typename T>
 __global__ void k_var_finish(const T* __restrict__ part, int ld, int ntiles, long rows, long m, long row0, T c,
-                             T* __restrict__ var, unsigned long long* __restrict__ n_below) {
+                             T* __restrict__ var, unsigned long long* __restrict__ n_below,
+                             const T* __restrict__ pmean, int nsplit, long pm_stride, T* __restrict__ mean) {
     long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows || row0 + r >= m) return;
+    if (pmean != nullptr) {  // mean partials of the column-split k* kernel, summed in split order
+        T mu = T(0);
+        for (int y = 0; y < nsplit; y++) mu += pmean[(long)y * pm_stride + r];
+        mean[row0 + r] = mu;
+    }
+    if (var == nullptr) return;
     T s = T(0);
     for (int t = 0; t < ntiles; t++) s += part[r * ld + t];
     const T min_noise = T(1e-5);

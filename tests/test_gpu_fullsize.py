@@ -72,8 +72,13 @@ def test_predict_chunking_and_subset_against_oracle(problem):
     mean, var = model.predict(xs)
     pick = np.array([0, 1, 32767, 32768, 65535, 65536, m - 1])
     mean_s, var_s = model.predict(xs[pick])
-    np.testing.assert_array_equal(mean[pick], mean_s)  # same rows, different chunk position: bit-identical
-    np.testing.assert_array_equal(var[pick], var_s)
+    # same rows through the throughput path (chunked GEMM) and through the small-batch latency path: the
+    # summation orders differ, the values agree to rounding
+    np.testing.assert_allclose(mean[pick], mean_s, rtol=0, atol=1e-13 * np.abs(mean).max())
+    np.testing.assert_allclose(var[pick], var_s, rtol=0, atol=1e-13)
+    again_mean, again_var = model.predict(xs)
+    np.testing.assert_array_equal(again_mean, mean)  # run-to-run bit reproducible
+    np.testing.assert_array_equal(again_var, var)
     kern = oracle_kernel(theta)
     var_ref = np.zeros(len(pick))
     mean_ref = ogpr.predict(kern, model.alpha, xs[pick], x, model.k_inv, var_ref)

@@ -175,3 +175,31 @@ def test_inverse_round_trip_n1024():
     assert np.abs(out["w"] @ k @ out["w"].T - np.eye(n)).max() < 1e-10  # W = L^-1  <=>  W K W^T = I
     assert np.abs(out["w"].T @ out["w"] - out["kinv"]).max() < 1e-10 * np.abs(out["kinv"]).max()
     assert np.abs(out["kinv"] @ k - np.eye(n)).max() < 1e-9
+
+
+@pytest.mark.parametrize("A", [np.float64, np.float32])
+def test_small_batch_predict_path_matches_throughput_path_and_oracle(A):
+    """m <= 64 takes the latency path (k_kstar_small / k_wmatvec_small), larger batches the GEMM path; both must
+    agree with each other and with the oracle, for every m around the switch."""
+    n, d = 300, 5
+    x, y = synth(n, d, A=A)
+    theta = random_thetas(1, d, seed=21, noise=(5e-2, 0.3) if A == np.float64 else (0.1, 0.5))[0]
+    xs = np.random.default_rng(4).random((200, d)).astype(A)
+    ref = oracle_lml(theta, x, y, A=A)
+    var_ref = np.zeros(200, dtype=A)
+    mean_ref = ogpr.predict(oracle_kernel(theta), ref.alpha, xs, x, ref.factorization.invc(), var_ref, A)
+    tol = TOL[A]
+    c = math.exp(theta[1])
+    with _ctx(A) as ctx:
+        ctx.set_data(x, y)
+        model = ctx.model(theta)
+        mean_big, var_big = model.predict(xs)
+        for m in (1, 2, 15, 16, 17, 63, 64, 65):
+            mean, var = model.predict(xs[:m])
+            np.testing.assert_allclose(mean, mean_ref[:m], rtol=0, atol=tol * max(1.0, np.abs(mean_ref).max()))
+            np.testing.assert_allclose(var, var_ref[:m], rtol=0, atol=tol * (c + 1e-5))
+            np.testing.assert_allclose(mean, mean_big[:m], rtol=0, atol=tol * 1e-2 * max(1.0, np.abs(mean_ref).max()))
+            np.testing.assert_allclose(var, var_big[:m], rtol=0, atol=tol * 1e-2 * (c + 1e-5))
+            mean_only, none = model.predict(xs[:m], want_variance=False)
+            np.testing.assert_array_equal(mean_only, mean)
+            assert none is None
