@@ -45,10 +45,21 @@ def parse():
     return ap.parse_args()
 
 
+def synth(n, d, seed=1, A=np.float64):
+    """X ~ U[0,1)^{n x d}; y = sum_k sin(2 pi x_k) + 0.1 N(0,1), normalised like the linear YNormalize
+    (ynormalize.rs:168-173) so that mean(y) = 1.05.  (Same generator as tests/util.py; kept here so that the GPU
+    arm of the benchmark imports nothing from tests/ or oracle/.)"""
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, d))
+    y = np.sin(2 * np.pi * x).sum(axis=1) + 0.1 * rng.standard_normal(n)
+    y = y - y.min()
+    y = y / (y.mean() if y.mean() > 0 else 1.0) + 0.05
+    return x.astype(A), y.astype(A)
+
+
 def workload(args):
     """X ~ U[0,1)^{n x d}, y = sum sin(2 pi x_k) + 0.1 N(0,1) normalised like the
     linear YNormalize; bounds as EstimatorGPR::new except noise in [1e-2, 1e1]."""
-    from tests.util import synth
     A = np.float64 if args.dtype == "f64" else np.float32
     x, y = synth(args.n, args.d, seed=1, A=A)
     p = args.d + 2
@@ -124,7 +135,8 @@ class ClockSampler:
 
 def oracle_eval_seconds(x, y, theta, A):
     """One reference-faithful LML + gradient evaluation on the host (oracle: full-square kernel,
-    materialised (n, n, d+1) gradient tensor, explicit potri), timed."""
+    materialised (n, n, d+1) gradient tensor, explicit potri), timed.  The ONLY place bench.py touches oracle/
+    (cpu_baseline leg and --impl reference)."""
     from tests.util import oracle_lml
     t0 = time.perf_counter()
     res = oracle_lml(theta, x, y, A=A)
@@ -319,13 +331,12 @@ def main():
     # ---- the whole north-star job once: fit (B lockstep runs, <= maxeval evaluations each) + predict
     full = None
     if not args.no_full_fit:
-        from oracle.rng import RNG  # start points only: reference draw order (gradmin.rs:21-24)
         bv = h.BoundedValue
         kernel = h.Product(h.ConstantKernel(bv(math.sqrt(lo[1] * hi[1]), lo[1], hi[1])),
                            h.Matern(2.5, [bv(1.0, 1e-3, 1e3)] * d))
         barrier()
         t0 = time.perf_counter()
-        fk = h.FittedKernel.new(ctx, kernel, x, y, RNG.new_with_seed(1), args.restarts, bv(1.0, 1e-2, 1e1),
+        fk = h.FittedKernel.new(ctx, kernel, x, y, h.RNG.new_with_seed(1), args.restarts, bv(1.0, 1e-2, 1e1),
                                 maxeval=args.maxeval, shard=hd.sharded_fit_runs if world > 1 else None)
         barrier()
         t_fit = time.perf_counter() - t0

@@ -13,4 +13,6 @@ from .gpr import (BoundedValue, BoundsError, ConstantKernel, Context, FittedKern
 from .estimator import (LINEAR, LOGARITHMIC, EstimatorGPR, SummaryStatistics, SurrogateModelGPR, YNormalize,  # noqa: F401
                         estimate_amplitude, expected_improvement)
 
+from .random import RNG  # noqa: F401
+
 __version__ = lib.hbegp_version().decode()

@@ -98,3 +98,27 @@ def test_kernel_parameter_objects_mirror_the_reference():
     assert k2.k1.constant.value == 5.0 and k2.k2.length_scale[0].value == 0.05
     with pytest.raises(h.BoundsError):
         k.with_theta([math.log(9.0), 0.0, 0.0])
+
+
+def test_python_rng_mirror_matches_oracle_stream():
+    import hbetune_rs_b200 as h
+    a, b = h.RNG.new_with_seed(123), RNG.new_with_seed(123)
+    assert a.state == b.s
+    fa, fb = a.fork_random_state(), b.fork_random_state()
+    assert fa.state == fb.s and a.state == b.s
+    assert [fa.uniform_inclusive(-11.5, 11.5) for _ in range(8)] == [fb.uniform_inclusive(-11.5, 11.5) for _ in range(8)]
+
+
+def test_gpu_arm_of_bench_does_not_import_the_oracle():
+    """Only the cpu_baseline / --impl reference legs may touch oracle/ (via tests.util, lazily)."""
+    import ast
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    top_level = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    names = [getattr(n, "module", None) or n.names[0].name for n in top_level]
+    assert not any(str(m).startswith(("oracle", "tests")) for m in names), names
+    for sub in ("hbetune_rs_b200",):
+        for fn in os.listdir(os.path.join(ROOT, sub)):
+            if fn.endswith(".py"):
+                text = open(os.path.join(ROOT, sub, fn)).read()
+                assert "import oracle" not in text and "from oracle" not in text, fn
