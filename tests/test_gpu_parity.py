@@ -203,3 +203,28 @@ def test_small_batch_predict_path_matches_throughput_path_and_oracle(A):
             mean_only, none = model.predict(xs[:m], want_variance=False)
             np.testing.assert_array_equal(mean_only, mean)
             assert none is None
+
+
+def test_workspace_limit_chunks_the_batch_bit_identically():
+    """A batch larger than the workspace capacity is evaluated in chunks; results do not depend on the chunking."""
+    import hbetune_rs_b200 as h
+    n, d = 1500, 4
+    x, y = synth(n, d)
+    thetas = random_thetas(7, d, seed=9)
+    with _ctx(np.float64) as ctx:
+        ctx.set_data(x, y)
+        a, ga, sa = ctx.lml_grad_batch(thetas)
+    with _ctx(np.float64) as ctx:
+        per_slot = 2 * 1536 * 1536 * 8
+        ctx.set_workspace_limit(3 * per_slot + (64 << 20))  # room for 3 of the 7 evaluations at a time
+        ctx.set_data(x, y)
+        b, gb, sb = ctx.lml_grad_batch(thetas)
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(ga, gb)
+        np.testing.assert_array_equal(sa, sb)
+    with _ctx(np.float64) as ctx:
+        ctx.set_workspace_limit(1 << 20)  # not even one n x n evaluation fits
+        ctx.set_data(x, y)
+        with pytest.raises(h.HbegpError) as e:
+            ctx.lml_grad_batch(thetas[:1])
+        assert e.value.code == -3
