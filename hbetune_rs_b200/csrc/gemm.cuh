@@ -181,8 +181,8 @@ __global__ void __launch_bounds__(GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR,
 
     const int lr = lane >> 2, lc = lane & 3;
     // warp-tile-relative row of accumulator slot i / column of slot j (see the two micro-kernels below)
-    auto row_of = [&](int i) { return (F64 || A_KMAJOR) ? i * 8 + lr : 4 * lr + i; };
-    auto col_of = [&](int j) { return F64 ? j * 8 + 2 * lc : (B_KMAJOR ? j * 4 + lc : 8 * lc + j); };
+    auto row_of = [&](int i) { return (F64 || A_KMAJOR) ? i * 8 + lr : FM * lr + i; };
+    auto col_of = [&](int j) { return F64 ? j * 8 + 2 * lc : (B_KMAJOR ? j * 4 + lc : FN * lc + j); };
     for (int kt = 0; kt < nk; kt++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -211,49 +211,50 @@ __global__ void __launch_bounds__(GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR,
                     for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
         } else {
-            // FP32 (FFMA): 4 x 8 outputs per thread, operands fetched four k at a time with 16-byte shared loads
-            // (12 LDS.128 per 128 FFMA).  Thread-to-row/column mapping follows the contiguous direction of the
-            // staged tile: k-major tiles give rows lr + 8 i / columns lc + 4 j, row-major tiles give the
-            // contiguous groups 4 lr + i / 8 lc + j.
-            static_assert(F64 || (FM == 4 && FN == 8), "f32 micro-kernel is written for 32x32 warp tiles");
+            // FP32 (FFMA): (WM/8) x (WN/4) outputs per thread — 4 x 8 for the 64x64 tile, 8 x 8 for 128x128 —
+            // operands fetched four k at a time with 16-byte shared loads.  Thread-to-row/column mapping follows
+            // the contiguous direction of the staged tile: k-major tiles give rows lr + 8 i / columns lc + 4 j,
+            // row-major tiles give the contiguous groups FM lr + i / FN lc + j.
+            static_assert(F64 || (FM % 4 == 0 && FN % 4 == 0), "f32 micro-kernel needs FM, FN multiples of 4");
 #pragma unroll
             for (int k4 = 0; k4 < BK; k4 += 4) {
-                float av[4][4], bv[8][4];
+                float av[FM][4], bv[FN][4];
                 if (A_KMAJOR) {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
+                    for (int i = 0; i < FM; i++) {
                         const float4 t = *reinterpret_cast<const float4*>(&sA[(wm * WM + i * 8 + lr) * Cfg::A_STRIDE + k4]);
                         av[i][0] = t.x; av[i][1] = t.y; av[i][2] = t.z; av[i][3] = t.w;
                     }
                 } else {
 #pragma unroll
-                    for (int kk = 0; kk < 4; kk++) {
-                        const float4 t = *reinterpret_cast<const float4*>(&sA[(k4 + kk) * Cfg::A_STRIDE + wm * WM + 4 * lr]);
-                        av[0][kk] = t.x; av[1][kk] = t.y; av[2][kk] = t.z; av[3][kk] = t.w;
-                    }
+                    for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+                        for (int i4 = 0; i4 < FM; i4 += 4) {
+                            const float4 t = *reinterpret_cast<const float4*>(&sA[(k4 + kk) * Cfg::A_STRIDE + wm * WM + FM * lr + i4]);
+                            av[i4][kk] = t.x; av[i4 + 1][kk] = t.y; av[i4 + 2][kk] = t.z; av[i4 + 3][kk] = t.w;
+                        }
                 }
                 if (B_KMAJOR) {
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
+                    for (int j = 0; j < FN; j++) {
                         const float4 t = *reinterpret_cast<const float4*>(&sB[(wn * WN + j * 4 + lc) * Cfg::B_STRIDE + k4]);
                         bv[j][0] = t.x; bv[j][1] = t.y; bv[j][2] = t.z; bv[j][3] = t.w;
                     }
                 } else {
 #pragma unroll
-                    for (int kk = 0; kk < 4; kk++) {
-                        const float4 t0 = *reinterpret_cast<const float4*>(&sB[(k4 + kk) * Cfg::B_STRIDE + wn * WN + 8 * lc]);
-                        const float4 t1 = *reinterpret_cast<const float4*>(&sB[(k4 + kk) * Cfg::B_STRIDE + wn * WN + 8 * lc + 4]);
-                        bv[0][kk] = t0.x; bv[1][kk] = t0.y; bv[2][kk] = t0.z; bv[3][kk] = t0.w;
-                        bv[4][kk] = t1.x; bv[5][kk] = t1.y; bv[6][kk] = t1.z; bv[7][kk] = t1.w;
-                    }
+                    for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+                        for (int j4 = 0; j4 < FN; j4 += 4) {
+                            const float4 t = *reinterpret_cast<const float4*>(&sB[(k4 + kk) * Cfg::B_STRIDE + wn * WN + FN * lc + j4]);
+                            bv[j4][kk] = t.x; bv[j4 + 1][kk] = t.y; bv[j4 + 2][kk] = t.z; bv[j4 + 3][kk] = t.w;
+                        }
                 }
 #pragma unroll
                 for (int kk = 0; kk < 4; kk++)
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
+                    for (int i = 0; i < FM; i++)
 #pragma unroll
-                        for (int j = 0; j < 8; j++)
-                            acc[i % FM][j % FN][0] = fmaf(av[i][kk], bv[j][kk], acc[i % FM][j % FN][0]);
+                        for (int j = 0; j < FN; j++) acc[i][j][0] = fmaf(av[i][kk], bv[j][kk], acc[i][j][0]);
             }
         }
     }
@@ -339,17 +340,27 @@ inline int& gemm_tile_pref() {
     return pref;
 }
 
-inline int pick_gemm_tile(int M, int N) {
-    return (gemm_tile_pref() == 128 && M % 128 == 0 && N % 128 == 0) ? 128 : 64;
+// f32: the 128x128 configuration (8 x 8 outputs per thread) has the better FFMA-to-load ratio on paper but
+// measures slower than 64x64 (north-star step 124.7 ms vs 113.8 ms, predict 455 vs 413 ms), so 64x64 is the
+// default here too; HBEGP_TILE32=128 selects the large tile.
+inline int& gemm_tile_pref_f32() {
+    static int pref = 64;
+    return pref;
 }
 
-// warp-tile height of the optional 128x128 configuration: 64x32 DMMA warp tiles for f64, 32x32 FFMA for f32
+template <typename T = double>
+inline int pick_gemm_tile(int M, int N) {
+    const int pref = std::is_same<T, float>::value ? gemm_tile_pref_f32() : gemm_tile_pref();
+    return (pref == 128 && M % 128 == 0 && N % 128 == 0) ? 128 : 64;
+}
+
+// warp-tile height of the 128x128 configuration: 64x32 warp tiles (f64: 8 x 4 DMMA tiles; f32: 8 x 8 per thread)
 template <typename T>
-constexpr int wm128() { return std::is_same<T, double>::value ? 64 : 32; }
+constexpr int wm128() { return 64; }
 
 template <typename T, bool AK, bool BK_>
 inline cudaError_t launch_gemm(const GemmArgs<T>& a, int batch, cudaStream_t stream) {
-    if (pick_gemm_tile(a.M, a.N) == 128) return launch_gemm_cfg<T, 128, 128, wm128<T>(), 32, AK, BK_>(a, batch, stream);
+    if (pick_gemm_tile<T>(a.M, a.N) == 128) return launch_gemm_cfg<T, 128, 128, wm128<T>(), 32, AK, BK_>(a, batch, stream);
     return launch_gemm_cfg<T, 64, 64, 32, 32, AK, BK_>(a, batch, stream);
 }
 

@@ -625,7 +625,7 @@ struct ModelT : Model {
             return HBEGP_OK;
         }
         const int chunk = (int)std::min<long>(predict_chunk_rows(), round_up(m, 128));
-        const int bn = pick_gemm_tile(128, np);  // rows are always a multiple of 128
+        const int bn = pick_gemm_tile<T>(128, np);  // rows are always a multiple of 128
         const int ntile = np / bn;
         if ((rc = kstar.ensure((size_t)chunk * np * sizeof(T)))) return rc;
         if ((rc = part.ensure((size_t)chunk * ntile * sizeof(T)))) return rc;
@@ -968,6 +968,7 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
     bool forced = false;
     if (const char* s = getenv("HBEGP_STREAMS")) { nsub = std::max(1, std::min(16, atoi(s))); forced = true; }
     if (const char* s = getenv("HBEGP_TILE")) gemm_tile_pref() = (atoi(s) == 128) ? 128 : 64;
+    if (const char* s = getenv("HBEGP_TILE32")) gemm_tile_pref_f32() = (atoi(s) == 128) ? 128 : 64;
     bool graphs_on = true;
     if (const char* s = getenv("HBEGP_GRAPHS")) graphs_on = atoi(s) != 0;
     if (dtype == HBEGP_F64) { static_cast<Engine<double>*>(e)->streams_forced = forced; static_cast<Engine<double>*>(e)->use_graphs = graphs_on; }
