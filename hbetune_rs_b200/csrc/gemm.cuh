@@ -15,6 +15,14 @@
 #include <stdint.h>
 #include <type_traits>
 
+// k depth of one pipeline stage and number of stages (probes/gemm_bench.cu: 16 x 3 and 32 x 2 are within 0.5 %)
+#ifndef HBEGP_BK
+#define HBEGP_BK 16
+#endif
+#ifndef HBEGP_STAGES
+#define HBEGP_STAGES 3
+#endif
+
 namespace hbegp {
 
 enum KMode : int {
@@ -59,7 +67,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-template <typename T, int BM, int BN, int WM, int WN, bool A_KMAJOR, bool B_KMAJOR, int BK_ = 16, int STAGES_ = 3>
+template <typename T, int BM, int BN, int WM, int WN, bool A_KMAJOR, bool B_KMAJOR, int BK_ = HBEGP_BK, int STAGES_ = HBEGP_STAGES>
 struct GemmCfg {
     static constexpr int BK = BK_;
     static constexpr int PAD = 4;
@@ -99,7 +107,7 @@ __device__ __forceinline__ void load_tile(T* __restrict__ s, const T* __restrict
     }
 }
 
-template <typename T, int BM, int BN, int WM, int WN, bool A_KMAJOR, bool B_KMAJOR, int BK_ = 16, int STAGES_ = 3>
+template <typename T, int BM, int BN, int WM, int WN, bool A_KMAJOR, bool B_KMAJOR, int BK_ = HBEGP_BK, int STAGES_ = HBEGP_STAGES>
 __global__ void __launch_bounds__(GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR, BK_, STAGES_>::THREADS)
     gemm_kernel(const GemmArgs<T> p) {
     using Cfg = GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR, BK_, STAGES_>;
