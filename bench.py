@@ -411,6 +411,15 @@ def main():
                 "sample": f"1 of the {B} LML+gradient evaluations of one step (n={n}, d={d}), reference-faithful restatement "
                           f"oracle (NumPy + OpenBLAS potrf/potrs/potri, (n,n,d+1) tensor materialised): {dt:.1f} s",
             }
+            try:
+                # the reference builds OpenBLAS single-threaded (Makefile:3-4, USE_THREAD=0): same evaluation on 1 thread
+                from threadpoolctl import threadpool_limits
+                with threadpool_limits(limits=1):
+                    dt1, _ = oracle_eval_seconds(x, y, thetas[0], A)
+                out["cpu_baseline"]["reference_equivalent_1_thread"] = {"value": 1.0 / dt1, "unit": "evals/s", "cores": 1,
+                                                                         "seconds_per_eval": dt1}
+            except ImportError:
+                pass
         print(json.dumps(out), flush=True)
     model.close()
     ctx.close()
