@@ -32,10 +32,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=4096)
-    ap.add_argument("--d", type=int, default=16)
+    # long spellings for use under torchrun, whose own parser treats --n / --m as ambiguous abbreviations
+    ap.add_argument("--n", "--train-n", dest="n", type=int, default=4096)
+    ap.add_argument("--d", "--feat-d", dest="d", type=int, default=16)
     ap.add_argument("--restarts", type=int, default=64)
-    ap.add_argument("--m", type=int, default=1 << 20)
+    ap.add_argument("--m", "--cand-m", dest="m", type=int, default=1 << 20)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-full-fit", action="store_true", help="skip the whole fit+predict wall-time leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
