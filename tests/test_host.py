@@ -122,3 +122,52 @@ def test_gpu_arm_of_bench_does_not_import_the_oracle():
             if fn.endswith(".py"):
                 text = open(os.path.join(ROOT, sub, fn)).read()
                 assert "import oracle" not in text and "from oracle" not in text, fn
+
+
+def test_c_abi_rejects_bad_arguments_without_crashing():
+    """Every entry point returns a status (< 0 with a message) instead of aborting."""
+    from hbetune_rs_b200 import _lib
+    L = _lib.lib
+    null = None
+    assert L.hbegp_set_data(null, 10, 2, null, null) == _lib.ERR_INVALID
+    assert b"null context" in L.hbegp_last_error()
+    assert L.hbegp_lml_grad_batch(null, 2.5, 1, null, null, null, null, null, null) == _lib.ERR_INVALID
+    assert L.hbegp_fit_runs(null, 2.5, 1, null, null, null, 150, None, null) == _lib.ERR_INVALID
+    assert L.hbegp_predict(null, 1, null, null, null, None) == _lib.ERR_INVALID
+    assert L.hbegp_predict_device(null, 1, null, null, null, null) == _lib.ERR_INVALID
+    assert L.hbegp_predict_mean_ei(null, None, 1, null, 0.0, null, null, None, None) == _lib.ERR_INVALID
+    assert L.hbegp_ctx_destroy(null) == 0 and L.hbegp_model_destroy(null) == 0  # destroying nothing is fine
+    assert L.hbegp_ctx_launch_count(null) == 0
+    h = C.c_void_p()
+    assert L.hbegp_ctx_create(0, 7, None, C.byref(h)) == _lib.ERR_INVALID  # bad dtype, checked before CUDA
+    assert L.hbegp_ctx_create(0, 0, None, None) == _lib.ERR_INVALID
+    x = (C.c_double * 2)(0.0, 0.0)
+    assert L.hbegp_minimize_by_gradient(_lib.OBJECTIVE_FN(lambda a, b, c: 0.0), None, 0, x, x, x, 10, None) == _lib.ERR_INVALID
+    yn = _lib.YNorm()
+    y = np.ones(3)
+    assert L.hbegp_ynorm_fit(0, 5, 3, y.ctypes.data_as(C.c_void_p), None, y.ctypes.data_as(C.c_void_p), C.byref(yn)) == _lib.ERR_INVALID
+    assert L.hbegp_estimate_amplitude(0, 0, None, None, None) == _lib.ERR_INVALID
+    res = (_lib.RunResult * 1)()
+    res[0].status = 1
+    assert L.hbegp_pick_best_run(1, res) == -1 and L.hbegp_pick_best_run(0, res) == -1
+
+
+def test_minimizer_respects_maxeval_and_bounds():
+    from hbetune_rs_b200 import _lib
+    calls = []
+
+    def f(xp, gp, _):
+        calls.append((xp[0], xp[1]))
+        gp[0], gp[1] = 2 * (xp[0] - 10.0), 2 * (xp[1] + 10.0)
+        return (xp[0] - 10.0) ** 2 + (xp[1] + 10.0) ** 2
+
+    x = np.array([0.0, 0.0])
+    lo, hi = np.array([-1.0, -2.0]), np.array([3.0, 2.0])
+    fout = C.c_double()
+    n = _lib.lib.hbegp_minimize_by_gradient(_lib.OBJECTIVE_FN(f), None, 2, x.ctypes.data_as(C.c_void_p),
+                                            lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), 7, C.byref(fout))
+    assert 1 <= n <= 7 and len(calls) == n
+    assert all(lo[0] <= a <= hi[0] and lo[1] <= b <= hi[1] for a, b in calls)  # never evaluated outside the box
+    n = _lib.lib.hbegp_minimize_by_gradient(_lib.OBJECTIVE_FN(f), None, 2, x.ctypes.data_as(C.c_void_p),
+                                            lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), 150, C.byref(fout))
+    assert list(x) == [3.0, -2.0] and fout.value == 49.0 + 64.0  # the constrained optimum is the corner
