@@ -353,10 +353,17 @@ __global__ void __launch_bounds__(256) k_grad_contract(const T* __restrict__ Kin
     }
     if (tid < TILE) ai[tid] = alpha[(long)b * astride + i0 + tid];
     else if (tid < 2 * TILE) aj[tid - TILE] = alpha[(long)b * astride + j0 + tid - TILE];
-    __syncthreads();
-    const T noise = prm[(long)b * pstride + 0], c = prm[(long)b * pstride + 1];
     const int tx = tid & 15, ty = tid >> 4;
     const T* Kb = Kinv + (long)b * mstride;
+    // the 16 K^-1 entries of this thread, requested up front so that their DRAM latency hides behind the shared
+    // memory fill and the distance loop (ncu: long_scoreboard was the top stall with the loads at the point of use)
+    T kv[16];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) kv[a * 4 + q] = Kb[(long)(i0 + ty + 16 * a) * np + j0 + tx + 16 * q];
+    __syncthreads();
+    const T noise = prm[(long)b * pstride + 0], c = prm[(long)b * pstride + 1];
     T cm[16];
     double g_noise = 0.0, g_c = 0.0;
     {
@@ -386,7 +393,7 @@ __global__ void __launch_bounds__(256) k_grad_contract(const T* __restrict__ Kin
                 T wgt = T(2);
                 if (mt == nt) wgt = (li > lj) ? T(2) : ((li == lj) ? T(1) : T(0));
                 if (gi >= n || gj >= n) wgt = T(0);
-                const T tij = ai[li] * aj[lj] - Kb[(long)gi * np + gj];
+                const T tij = ai[li] * aj[lj] - kv[a * 4 + q];
                 const T s = S[a * 4 + q];
                 T base, dk_factor, kval;
                 if (NU2 == 5) {
