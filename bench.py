@@ -235,8 +235,11 @@ def main():
         local = np.concatenate([lml[:, None], grad, status[:, None].astype(np.float64)], axis=1)
         return hd.all_gather_array(local, counts)  # per-restart LML exchange (NCCL over NVLink)
 
+    x_pin = torch.from_numpy(x).pin_memory().numpy()  # pinned host staging for the end-to-end leg
+    y_pin = torch.from_numpy(y).pin_memory().numpy()
+
     def step_e2e():
-        ctx.set_data(x, y)  # host -> device copy of X, y every step
+        ctx.set_data(x_pin, y_pin)  # host -> device copy of X, y every step (theta goes up / results come back inside)
         return step_resident()
 
     def timed(fn, steps, warmup):
