@@ -83,3 +83,36 @@ def test_capture_is_best_over_all_evaluations():
     assert res[0].best_lml == res[1].best_lml and res[0].n_evals == res[1].n_evals  # identical runs
     assert best == int(np.argmax([r.best_lml for r in res]))  # first of the tied maxima
     assert not (best == 1)
+
+
+@pytest.mark.parametrize("n,d,restarts", [(40, 2, 2), (120, 3, 3)])
+def test_fit_f32_matches_f32_oracle_fit(n, d, restarts):
+    """--use-32: f32 data and linear algebra on both sides, same optimiser, same start points.  Measured
+    (probes/f32_fit_check.py): LML relative 5e-8..2e-7, theta 1e-4..3e-4 (ln units), mean 5e-5..1.3e-4; the bounds
+    below leave an order of magnitude for trajectory branching."""
+    import hbetune_rs_b200 as h
+    A = np.float32
+    x, y = synth(n, d, A=A)
+
+    def kernels(mod):
+        bv = mod.BoundedValue
+        return (mod.Product(mod.ConstantKernel(bv(1.0, 1e-2, 1e2)), mod.Matern(2.5, [bv(1.0, 1e-2, 1e2)] * d)),
+                bv(1.0, 1e-1, 1e1))
+
+    ok, onoise = kernels(ogpr)
+    ref = ogpr.fit_kernel(ok, x, y, RNG.new_with_seed(7), restarts, onoise, lib_minimizer(), A=A)
+    gk, gnoise = kernels(h)
+    with h.Context(0, h.F32) as ctx:
+        fk = h.FittedKernel.new(ctx, gk, x, y, h.RNG.new_with_seed(7), restarts, gnoise)
+        xs = np.random.default_rng(0).random((30, d)).astype(A)
+        var = np.zeros(30, dtype=A)
+        mean = h.predict(fk, xs, var)
+    assert mean.dtype == A and fk.alpha.dtype == A
+    assert abs(fk.lml - ref.lml) <= 1e-5 * abs(ref.lml)
+    th_gpu = np.array([math.log(fk.noise.value)] + fk.kernel.theta())
+    th_ref = np.array([math.log(ref.noise.value)] + ref.kernel.theta())
+    np.testing.assert_allclose(th_gpu, th_ref, rtol=0, atol=3e-3)
+    var_ref = np.zeros(30, dtype=A)
+    mean_ref = ogpr.predict(ref.kernel, ref.alpha, xs, x, ref.k_inv, var_ref, A)
+    np.testing.assert_allclose(mean, mean_ref, rtol=0, atol=1e-3 * max(1.0, np.abs(mean_ref).max()))
+    np.testing.assert_allclose(var, var_ref, rtol=0, atol=3e-4)
