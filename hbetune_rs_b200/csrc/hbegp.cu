@@ -76,6 +76,13 @@ struct EngineBase {
     bool own_stream = false;
     std::vector<cudaStream_t> sub;
     std::vector<cudaEvent_t> sub_done;
+    // side stream + two events per group: the inverse-merge product T = L21 W11 of a node runs beside its trailing
+    // update (both only read L21); used where the launch sequence is a captured graph (n <= 2048)
+    std::vector<cudaStream_t> side;
+    std::vector<cudaEvent_t> side_a, side_b;
+    cudaStream_t main_side = nullptr;
+    cudaEvent_t main_a = nullptr, main_b = nullptr;
+    bool use_side = true;
     cudaEvent_t fork_ev = nullptr;
     long n = 0;
     int d = 0, np = 0;
@@ -266,7 +273,12 @@ struct Engine : EngineBase {
     }
 
     // ---------------------------------------------------------------- recursive Cholesky + inverse
-    int chol_inv(cudaStream_t st, int s0, int cnt, int r0, int s) {
+    struct Side {
+        cudaStream_t st = nullptr;
+        cudaEvent_t a = nullptr, b = nullptr;
+    };
+
+    int chol_inv(cudaStream_t st, int s0, int cnt, int r0, int s, Side sd = Side()) {
         T* Ab = (T*)A.p + (size_t)s0 * mstride();
         T* Wb = (T*)W.p + (size_t)s0 * mstride();
         if (s == TILE) {
@@ -281,7 +293,7 @@ struct Engine : EngineBase {
         if (q1 >= q) q1 = q - 1;
         const int s1 = q1 * TILE, s2 = s - s1;
         int rc;
-        if ((rc = chol_inv(st, s0, cnt, r0, s1))) return rc;
+        if ((rc = chol_inv(st, s0, cnt, r0, s1, sd))) return rc;
         T* A21 = Ab + (long)(r0 + s1) * np + r0;
         T* W21 = Wb + (long)(r0 + s1) * np + r0;
         T* W11 = Wb + (long)r0 * np + r0;
@@ -295,15 +307,24 @@ struct Engine : EngineBase {
         g.A = A21; g.B = W11; g.C = W21; g.M = s2; g.N = s1; g.K = s1; g.kmode = K_LE_N; g.lower_only = 0;
         g.alpha = T(1); g.beta = T(0);
         CUDA_TRY((launch_gemm<T, true, true>(g, cnt, st))); launches++;
+        // 3. T = L21 W11 -> A(2,1); independent of step 2 and of the second half, so it may run on the side stream
+        cudaStream_t st3 = st;
+        if (sd.st) {
+            CUDA_TRY(cudaEventRecord(sd.a, st));
+            CUDA_TRY(cudaStreamWaitEvent(sd.st, sd.a, 0));
+            st3 = sd.st;
+        }
+        g.A = W21; g.B = W11; g.C = A21; g.M = s2; g.N = s1; g.K = s1; g.kmode = K_GE_N; g.lower_only = 0;
+        g.alpha = T(1); g.beta = T(0);
+        CUDA_TRY((launch_gemm<T, true, false>(g, cnt, st3))); launches++;
+        if (sd.st) CUDA_TRY(cudaEventRecord(sd.b, sd.st));
         // 2. trailing update: A22 -= L21 L21^T (lower tiles)
         g.A = W21; g.B = W21; g.C = A22; g.M = s2; g.N = s2; g.K = s1; g.kmode = K_FULL; g.lower_only = 1;
         g.alpha = T(-1); g.beta = T(1);
         CUDA_TRY((launch_gemm<T, true, true>(g, cnt, st))); launches++;
-        // 3. T = L21 W11 -> A(2,1)
-        g.A = W21; g.B = W11; g.C = A21; g.M = s2; g.N = s1; g.K = s1; g.kmode = K_GE_N; g.lower_only = 0;
-        g.alpha = T(1); g.beta = T(0);
-        CUDA_TRY((launch_gemm<T, true, false>(g, cnt, st))); launches++;
-        if ((rc = chol_inv(st, s0, cnt, r0 + s1, s2))) return rc;
+        if ((rc = chol_inv(st, s0, cnt, r0 + s1, s2, sd))) return rc;
+        // (a nested node may have re-recorded sd.b later on the side stream: waiting for that implies our product)
+        if (sd.st) CUDA_TRY(cudaStreamWaitEvent(st, sd.b, 0));
         // 4. W21 = -W22 T
         g.A = W22; g.B = A21; g.C = W21; g.M = s2; g.N = s1; g.K = s2; g.kmode = K_LE_M; g.lower_only = 0;
         g.alpha = T(-1); g.beta = T(0);
@@ -328,7 +349,7 @@ struct Engine : EngineBase {
     int phase = 3;
 
     template <int NU2>
-    int pipeline_nu(cudaStream_t st, int s0, int cnt, bool want_grad, bool want_kinv) {
+    int pipeline_nu(cudaStream_t st, int s0, int cnt, bool want_grad, bool want_kinv, Side sd) {
         T* Ab = (T*)A.p + (size_t)s0 * mstride();
         T* Wb = (T*)W.p + (size_t)s0 * mstride();
         T* xs = (T*)xsT.p + (size_t)s0 * d * np;
@@ -345,7 +366,7 @@ struct Engine : EngineBase {
         CUDA_TRY(cudaGetLastError());
         if (phase < 1) return HBEGP_OK;
         int rc;
-        if ((rc = chol_inv(st, s0, cnt, 0, np))) return rc;
+        if ((rc = chol_inv(st, s0, cnt, 0, np, sd))) return rc;
         if (phase < 2) return HBEGP_OK;
         // alpha = W^T (W y)   (lml.rs:54 solves K alpha = y through the factorisation)
         k_trmv_lower<T><<<dim3(np / 8, 1, cnt), 256, 0, st>>>(Wb, mstride(), np, (const T*)dY.p, 0, ub, np);
@@ -372,10 +393,11 @@ struct Engine : EngineBase {
         return HBEGP_OK;
     }
 
-    int pipeline(int nu2, cudaStream_t st, int s0, int cnt, bool want_grad, bool want_kinv) {
-        if (nu2 == 5) return pipeline_nu<5>(st, s0, cnt, want_grad, want_kinv);
-        if (nu2 == 3) return pipeline_nu<3>(st, s0, cnt, want_grad, want_kinv);
-        return pipeline_nu<1>(st, s0, cnt, want_grad, want_kinv);
+    int pipeline(int nu2, cudaStream_t st, int s0, int cnt, bool want_grad, bool want_kinv, Side sd = Side()) {
+        if (!(use_side && np <= 2048 && np > TILE)) sd = Side();  // large n: the GEMMs fill the GPU on their own
+        if (nu2 == 5) return pipeline_nu<5>(st, s0, cnt, want_grad, want_kinv, sd);
+        if (nu2 == 3) return pipeline_nu<3>(st, s0, cnt, want_grad, want_kinv, sd);
+        return pipeline_nu<1>(st, s0, cnt, want_grad, want_kinv, sd);
     }
 
     int n_groups(int cnt) const {
@@ -395,7 +417,9 @@ struct Engine : EngineBase {
         CUDA_TRY(cudaMemsetAsync(d_status.p, 0, (size_t)cnt * sizeof(int), stream));
         const int groups = n_groups(cnt);
         if (groups <= 1) {
-            int rc = pipeline(nu2, stream, 0, cnt, want_grad, want_kinv);
+            Side sd;
+            sd.st = main_side; sd.a = main_a; sd.b = main_b;
+            int rc = pipeline(nu2, stream, 0, cnt, want_grad, want_kinv, sd);
             if (rc) return rc;
         } else {
             CUDA_TRY(cudaEventRecord(fork_ev, stream));
@@ -403,7 +427,9 @@ struct Engine : EngineBase {
             for (int g = 0; g < groups; g++) {
                 int c = base + (g < extra ? 1 : 0);
                 CUDA_TRY(cudaStreamWaitEvent(sub[g], fork_ev, 0));
-                int rc = pipeline(nu2, sub[g], s0, c, want_grad, want_kinv);
+                Side sd;
+                sd.st = side[g]; sd.a = side_a[g]; sd.b = side_b[g];
+                int rc = pipeline(nu2, sub[g], s0, c, want_grad, want_kinv, sd);
                 if (rc) return rc;
                 CUDA_TRY(cudaEventRecord(sub_done[g], sub[g]));
                 CUDA_TRY(cudaStreamWaitEvent(stream, sub_done[g], 0));
@@ -983,8 +1009,26 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
         }
         e->sub.push_back(s);
         e->sub_done.push_back(ev);
+        cudaStream_t s2;
+        cudaEvent_t ea, eb;
+        if (cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ea, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&eb, cudaEventDisableTiming) != cudaSuccess) {
+            delete e;
+            return fail(HBEGP_ERR_CUDA, "ctx_create: could not create side streams");
+        }
+        e->side.push_back(s2);
+        e->side_a.push_back(ea);
+        e->side_b.push_back(eb);
     }
     if (cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming) != cudaSuccess) { delete e; return fail(HBEGP_ERR_CUDA, "ctx_create: event"); }
+    if (cudaStreamCreateWithFlags(&e->main_side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->main_a, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->main_b, cudaEventDisableTiming) != cudaSuccess) {
+        delete e;
+        return fail(HBEGP_ERR_CUDA, "ctx_create: side stream");
+    }
+    if (const char* s = getenv("HBEGP_SIDE")) e->use_side = atoi(s) != 0;
     *out = new hbegp_ctx{e};
     return HBEGP_OK;
 }
@@ -1001,6 +1045,12 @@ int hbegp_ctx_destroy(hbegp_ctx* ctx) {
     e->models.clear();
     for (auto s : e->sub) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     for (auto ev : e->sub_done) cudaEventDestroy(ev);
+    for (auto s2 : e->side) { cudaStreamSynchronize(s2); cudaStreamDestroy(s2); }
+    for (auto ev : e->side_a) cudaEventDestroy(ev);
+    for (auto ev : e->side_b) cudaEventDestroy(ev);
+    if (e->main_side) { cudaStreamSynchronize(e->main_side); cudaStreamDestroy(e->main_side); }
+    if (e->main_a) cudaEventDestroy(e->main_a);
+    if (e->main_b) cudaEventDestroy(e->main_b);
     if (e->fork_ev) cudaEventDestroy(e->fork_ev);
     if (e->own_stream) cudaStreamDestroy(e->stream);
     delete e;
