@@ -150,6 +150,7 @@ struct Engine : EngineBase {
     };
     std::map<std::tuple<int, int, int, int, int>, CachedGraph> graphs;
     bool use_graphs = true;
+    bool pad_batches = true;
     bool streams_forced = false;
     T* h_prm = nullptr;  // pinned staging
     double* h_out = nullptr;
@@ -492,11 +493,19 @@ struct Engine : EngineBase {
         if (B < 0 || (B > 0 && (!theta || !lml))) return fail(HBEGP_ERR_INVALID, "lml_grad_batch: bad arguments");
         if (B == 0) return HBEGP_OK;
         CUDA_TRY(cudaSetDevice(device));
-        if ((rc = ensure_capacity(B))) return rc;
+        if ((rc = ensure_capacity((use_graphs && pad_batches && np <= 2048 && B > 4) ? (B + 3) / 4 * 4 : B))) return rc;
         for (int b0 = 0; b0 < B; b0 += cap) {
             int cnt = std::min(cap, B - b0);
             for (int b = 0; b < cnt; b++) fill_params(theta + (size_t)(b0 + b) * p(), lo, hi, h_prm + (size_t)b * p());
-            if ((rc = run_chunk(nu2, cnt, grad != nullptr, false))) return rc;
+            // Where evaluations are replayed as CUDA graphs (small n, latency bound) a few extra matrices in grid.z
+            // cost next to nothing, while every distinct batch size costs a capture + instantiation: round the
+            // batch up to a multiple of 4 with copies of the last theta (their results are ignored).
+            int run = cnt;
+            if (use_graphs && pad_batches && np <= 2048 && cnt > 4) {
+                run = std::min(cap, (cnt + 3) / 4 * 4);
+                for (int b = cnt; b < run; b++) std::memcpy(h_prm + (size_t)b * p(), h_prm + (size_t)(cnt - 1) * p(), sizeof(T) * p());
+            }
+            if ((rc = run_chunk(nu2, run, grad != nullptr, false))) return rc;
             for (int b = 0; b < cnt; b++) {
                 bool bad = h_status[b] != 0 || !std::isfinite(h_out[b]);
                 lml[b0 + b] = bad ? -std::numeric_limits<double>::infinity() : h_out[b];
@@ -1029,6 +1038,11 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
         return fail(HBEGP_ERR_CUDA, "ctx_create: side stream");
     }
     if (const char* s = getenv("HBEGP_SIDE")) e->use_side = atoi(s) != 0;
+    if (const char* s = getenv("HBEGP_PAD")) {
+        const bool pad = atoi(s) != 0;
+        if (dtype == HBEGP_F64) static_cast<Engine<double>*>(e)->pad_batches = pad;
+        else static_cast<Engine<float>*>(e)->pad_batches = pad;
+    }
     *out = new hbegp_ctx{e};
     return HBEGP_OK;
 }
