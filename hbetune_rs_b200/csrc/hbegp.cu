@@ -283,7 +283,7 @@ struct Engine : EngineBase {
         T* Ab = (T*)A.p + (size_t)s0 * mstride();
         T* Wb = (T*)W.p + (size_t)s0 * mstride();
         if (s == TILE) {
-            k_leaf<T><<<dim3(1, 1, cnt), 256, 0, st>>>(Ab, Wb, mstride(), np, r0, (T*)ldp.p + (size_t)s0 * (np / TILE), np / TILE,
+            k_leaf<T><<<dim3(1, 1, cnt), 256, leaf_smem_bytes<T>(), st>>>(Ab, Wb, mstride(), np, r0, (T*)ldp.p + (size_t)s0 * (np / TILE), np / TILE,
                                                        (int*)d_status.p + s0);
             launches++;
             CUDA_TRY(cudaGetLastError());
@@ -855,6 +855,7 @@ static int configure_gemms() {
 #undef HBEGP_CFG
     // kernels whose dynamic shared memory grows with the feature count d (two d x 64 operand tiles)
     const int big = (int)kMaxFeatureSmem;
+    CUDA_TRY(cudaFuncSetAttribute(k_leaf<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem_bytes<T>()));
     CUDA_TRY(cudaFuncSetAttribute(k_assemble<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(k_assemble<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(k_assemble<T, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));

@@ -122,16 +122,16 @@ __global__ void __launch_bounds__(256) k_assemble(const T* __restrict__ xsT, int
 }
 
 // Reciprocal of a Cholesky pivot.  It sits on the 64-step critical path of the leaf, where an IEEE FP64
-// division costs ~8 dependent FP64 operations; a single-precision seed plus two Newton steps (4 dependent
-// DFMAs, relative error ~2^-52 for pivots inside the float range) halves that.
+// division costs ~8 dependent FP64 operations plus a slow-path branch; the hardware seed (rcp.approx.ftz.f64,
+// ~20 bits) plus two Newton steps (4 dependent DFMAs, relative error ~2^-52) halves that.
 template <typename T>
 __device__ __forceinline__ T pivot_rcp(T d);
 template <>
 __device__ __forceinline__ float pivot_rcp<float>(float d) { return 1.0f / d; }
 template <>
 __device__ __forceinline__ double pivot_rcp<double>(double d) {
-    if (!(d > 1e-30 && d < 1e30)) return 1.0 / d;
-    double r = (double)__frcp_rn((float)d);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));  // MUFU.RCP64H: ~20 bits, full exponent range
     double e = fma(-d, r, 1.0);
     r = fma(r, e, r);
     e = fma(-d, r, 1.0);
@@ -140,128 +140,145 @@ __device__ __forceinline__ double pivot_rcp<double>(double d) {
 }
 
 // Leaf of the recursive factorisation: 64x64 diagonal block at (r0, r0).  In: A block (lower part).
-// Out: L in the lower part of the A block, W = L^-1 as a full tile (zeros above the diagonal) in the
-// W buffer, sum_i ln L_ii in ldp[b][leaf], status[b] = 1 when a pivot is not positive (lml.rs:47-50).
+// Out: W = L^-1 as a full tile (zeros above the diagonal) in the W buffer (L itself is not needed again: the
+// parent nodes solve their panels with W), sum_i ln L_ii in ldp[b][leaf], status[b] = 1 when a pivot is not
+// positive (lml.rs:47-50).
 //
-// 16 x 16 threads; thread (tx, ty) keeps the 4 x 4 cells (ty + 16a, tx + 16q) in registers.  Both phases
-// are 64 sequential rank-1 steps with one barrier each: per step a thread gathers 4 + 4 operands from
-// shared memory and updates its live cells; only the cells another thread needs next (the next pivot
-// column / row) are written back to shared memory.
-template <typename T, int DBG = 0>  // DBG: probe-only switches (1: skip Cholesky loop, 2: skip Gauss-Jordan loop, 3: both)
+// The 64 pivots are inherently sequential and each step costs a barrier, a shared-memory round trip and an FP64
+// reciprocal, so the kernel keeps the per-pivot work minimal (blocked with nb = 16):
+//  * Cholesky on unscaled columns u_ij = L_ij L_jj (u_ik -= u_ij u_kj / u_jj): a pivot step only updates the
+//    remaining columns of its 16-wide panel (<= 4 cells per thread); the rest of the matrix gets one rank-16
+//    update per panel.  No square root on the pivot chain: 1 / L_jj = rsqrt(u_jj) for all j at the end.
+//  * inverse: the four 16x16 diagonal blocks are inverted side by side (15 steps instead of 63), the off-diagonal
+//    blocks follow by block forward substitution W_PQ = -W_PP sum_R L_PR W_RQ (three levels of small products).
+template <typename T>
+constexpr size_t leaf_smem_bytes() { return (2 * (size_t)TILE * (TILE + 1) + 2 * TILE) * sizeof(T); }
+
+template <typename T, int DBG = 0>  // DBG: probe-only switch (1: skip the Cholesky loops, 2: skip the inverse)
 __global__ void __launch_bounds__(256) k_leaf(T* __restrict__ A, T* __restrict__ W, long mstride, int np, int r0,
                                               T* __restrict__ ldp, int ldp_stride, int* __restrict__ status) {
-    __shared__ T as[TILE][TILE + 1];
-    __shared__ T dinv[TILE];
+    extern __shared__ __align__(16) unsigned char leaf_smem_raw[];
+    typedef T Row[TILE + 1];
+    Row* as = reinterpret_cast<Row*>(leaf_smem_raw);                                   // u (lower); scratch (upper)
+    Row* ws = reinterpret_cast<Row*>(leaf_smem_raw + sizeof(T) * TILE * (TILE + 1));   // W = L^-1
+    T* rdv = reinterpret_cast<T*>(leaf_smem_raw + 2 * sizeof(T) * TILE * (TILE + 1)); // 1 / u_jj
+    T* dinv = rdv + TILE;                                                              // 1 / L_jj
     __shared__ int fail;
     const int b = blockIdx.z, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     T* Ab = A + (long)b * mstride + (long)r0 * np + r0;
     T* Wb = W + (long)b * mstride + (long)r0 * np + r0;
     if (tid == 0) fail = 0;
-    T v[4][4];
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int i = ty + 16 * a, k = tx + 16 * q;
-            v[a][q] = (k <= i) ? Ab[(long)i * np + k] : T(0);
-            as[i][k] = v[a][q];
+            as[i][k] = (k <= i) ? Ab[(long)i * np + k] : T(0);
+            ws[i][k] = (i == k) ? T(1) : T(0);
         }
-    // --- right-looking Cholesky on unscaled columns: a_ik -= a_ij a_kj / a_jj; L[i][j] = a_ij / sqrt(a_jj)
-    //     goes to the upper part transposed (as[j][i]).
-    for (int j = 0; j < ((DBG & 1) ? 0 : TILE); j++) {
-        __syncthreads();
-        T dj = as[j][j];
-        if (!(dj > T(0)) || !(dj <= T(1e300))) {
-            if (tid == 0) fail = 1;
-            dj = T(1);
-        }
-        const T rd = pivot_rcp<T>(dj);
-        T li[4], lk[4];
+    // ---- blocked Cholesky (nb = 16) on unscaled columns
+    if (!(DBG & 1)) {
+        const int pi = tid >> 2, pq = tid & 3;  // panel phase: row pi, panel columns pq, pq + 4, pq + 8, pq + 12
+        for (int P = 0; P < 4; P++) {
+            const int c0 = 16 * P;
+            __syncthreads();
+            T pv[4];
 #pragma unroll
-        for (int a = 0; a < 4; a++) li[a] = as[ty + 16 * a][j];
+            for (int t = 0; t < 4; t++) pv[t] = as[pi][c0 + pq + 4 * t];
 #pragma unroll
-        for (int q = 0; q < 4; q++) lk[q] = as[tx + 16 * q][j];
+            for (int jj = 0; jj < 16; jj++) {
+                const int j = c0 + jj;
+                if (jj > 0) {
+                    // column j is final after step j - 1: its owners publish it for this step
+                    if (pq == (jj & 3)) as[pi][j] = pv[jj >> 2];
+                    __syncthreads();
+                }
+                T dj = as[j][j];
+                const T uij = as[pi][j];
+                T ukj[4];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            if (j < 16 * q + 15) {  // block column still has live cells (uniform branch)
+                for (int t = jj >> 2; t < 4; t++) ukj[t] = as[c0 + pq + 4 * t][j];
+                if (!(dj > T(0)) || !(dj <= T(1e300))) {
+                    if (tid == 0) fail = 1;
+                    dj = T(1);
+                }
+                const T rd = pivot_rcp<T>(dj);
+                if (tid == 0) rdv[j] = rd;
+                const T li = uij * rd;
 #pragma unroll
-                for (int a = q; a < 4; a++) {
-                    // branch-free: a select and a predicated store (divergent branch regions cost ~30 cycles each)
-                    const int i = ty + 16 * a, k = tx + 16 * q;
-                    const bool act = (k > j) & (k <= i);
-                    // the operand product does not wait for the pivot reciprocal: chain = rcp -> one FMA
-                    const T upd = fma(-(li[a] * lk[q]), rd, v[a][q]);
-                    v[a][q] = act ? upd : v[a][q];
-                    if (act & (k == j + 1)) as[i][k] = upd;  // next pivot column
+                for (int t = jj >> 2; t < 4; t++) {
+                    const int k = pq + 4 * t;  // panel-relative column
+                    if (k > jj && c0 + k <= pi) pv[t] = fma(-li, ukj[t], pv[t]);
+                }
+            }
+            __syncthreads();
+            // rank-16 update of everything right of the panel: u_ik -= sum_{j in panel} u_ij u_kj / u_jj
+#pragma unroll
+            for (int q = 1; q < 4; q++) {
+                if (q > P) {
+                    T lk[16];
+#pragma unroll
+                    for (int jj = 0; jj < 16; jj++) lk[jj] = as[tx + 16 * q][c0 + jj] * rdv[c0 + jj];
+#pragma unroll
+                    for (int a = 1; a < 4; a++) {
+                        if (a >= q) {
+                            const int i = ty + 16 * a, k = tx + 16 * q;
+                            T acc = T(0);
+#pragma unroll
+                            for (int jj = 0; jj < 16; jj++) acc = fma(as[i][c0 + jj], lk[jj], acc);
+                            if (k <= i) as[i][k] -= acc;
+                        }
+                    }
                 }
             }
         }
     }
     __syncthreads();
-    // The unscaled columns are final: scale them into L off the critical path (the square roots of all
-    // 64 pivots in parallel), L^T into the upper part: as[j][i] = L[i][j].
     if (tid < TILE) {
         T dj = as[tid][tid];
         if (!(dj > T(0)) || !(dj <= T(1e300))) dj = T(1);
-        dinv[tid] = T(1) / dev_sqrt<T>(dj);  // 1 / L[j][j]
+        dinv[tid] = T(1) / dev_sqrt<T>(dj);
+        if (DBG & 1) rdv[tid] = T(1) / dj;
     }
-    __syncthreads();
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int i = ty + 16 * a, k = tx + 16 * q;
-            if (k < i) as[k][i] = as[i][k] * dinv[k];
+    // ---- inverse of the four 16x16 diagonal blocks, side by side (rows unscaled: W_true = W_u * dinv_row)
+    if (!(DBG & 2)) {
+        const int P = tid >> 6, r = (tid & 63) >> 2, cq = tid & 3, c0 = 16 * P;
+        for (int kk = 0; kk < 15; kk++) {
+            __syncthreads();
+            if (r > kk) {
+                const T lik = as[c0 + r][c0 + kk] * rdv[c0 + kk];  // L_ik / L_kk = u_ik / u_kk
+                for (int c = cq; c <= kk; c += 4) ws[c0 + r][c0 + c] = fma(-lik, ws[c0 + kk][c0 + c], ws[c0 + r][c0 + c]);
+            }
         }
-    __syncthreads();
-    // --- L back to global (from the upper part), then W = L^-1 in the registers / lower part
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int i = ty + 16 * a, k = tx + 16 * q;
-            if (k < i) Ab[(long)i * np + k] = as[k][i];
-            else if (k == i) Ab[(long)i * np + k] = T(1) / dinv[i];
-        }
-    __syncthreads();
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int i = ty + 16 * a, k = tx + 16 * q;
-            v[a][q] = (i == k) ? T(1) : T(0);
-            if (k <= i) as[i][k] = v[a][q];
-        }
-    // --- Gauss-Jordan on [L | I]: rows i > k: W[i][j] -= L[i][k] * (W[k][j] / L[k][k]) for j <= k.
-    //     L[i][k] = as[k][i] (upper part), row k of W = as[k][0..k]; rows are scaled by 1/L[i][i] at the end.
-    for (int k = 0; k < ((DBG & 2) ? 0 : TILE - 1); k++) {
         __syncthreads();
-        const T rk = dinv[k];
-        T li[4], wk[4];
-#pragma unroll
-        for (int a = 0; a < 4; a++) li[a] = as[k][ty + 16 * a];
-#pragma unroll
-        for (int q = 0; q < 4; q++) wk[q] = as[k][tx + 16 * q] * rk;
-#pragma unroll
-        for (int a = 0; a < 4; a++) {
-            if (k < 16 * a + 15) {  // block row still has rows below k (uniform branch)
-#pragma unroll
-                for (int q = 0; q <= a; q++) {
-                    const int i = ty + 16 * a, jj = tx + 16 * q;
-                    const bool act = (i > k) & (jj <= k);
-                    const T upd = fma(-li[a], wk[q], v[a][q]);
-                    v[a][q] = act ? upd : v[a][q];
-                    if (act & (i == k + 1)) as[i][jj] = upd;  // next pivot row
-                }
+        {
+            const int i = c0 + r;
+            for (int c = cq; c <= r; c += 4) ws[i][c0 + c] *= dinv[i];
+        }
+        // ---- off-diagonal blocks by block forward substitution; S_PQ goes to the free upper part of `as`
+        const int sr = tid >> 4, sc = tid & 15;
+        for (int PP = 1; PP < 4; PP++) {
+            __syncthreads();
+            for (int Q = 0; Q < PP; Q++) {
+                T acc = T(0);
+                for (int k = 16 * Q; k < 16 * PP; k++) acc = fma(as[16 * PP + sr][k] * dinv[k], ws[k][16 * Q + sc], acc);
+                as[16 * Q + sr][16 * PP + sc] = acc;  // S_PQ (strictly upper position: Q < PP)
+            }
+            __syncthreads();
+            for (int Q = 0; Q < PP; Q++) {
+                T acc = T(0);
+                for (int k = 0; k <= sr; k++) acc = fma(ws[16 * PP + sr][16 * PP + k], as[16 * Q + k][16 * PP + sc], acc);
+                ws[16 * PP + sr][16 * Q + sc] = -acc;
             }
         }
     }
+    __syncthreads();
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int i = ty + 16 * a, k = tx + 16 * q;
-            Wb[(long)i * np + k] = (k <= i) ? v[a][q] * dinv[i] : T(0);
+            Wb[(long)i * np + k] = (k <= i) ? ws[i][k] : T(0);
         }
     if (tid < 32) {
         T s = T(0);

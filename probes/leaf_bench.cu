@@ -13,12 +13,13 @@ template <int DBG>
 float time_leaf(int B, double* A0, double* A, double* W, int np, double* ldp, int* st, int reps) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     size_t bytes = (size_t)B * np * np * 8;
+    CK(cudaFuncSetAttribute(k_leaf<double, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem_bytes<double>()));
     float total = 0;
     for (int r = 0; r < reps + 1; r++) {
         CK(cudaMemcpy(A, A0, bytes, cudaMemcpyDeviceToDevice));
         CK(cudaDeviceSynchronize());
         cudaEventRecord(e0);
-        k_leaf<double, DBG><<<dim3(1, 1, B), 256>>>(A, W, (long)np * np, np, 0, ldp, np / 64, st);
+        k_leaf<double, DBG><<<dim3(1, 1, B), 256, leaf_smem_bytes<double>()>>>(A, W, (long)np * np, np, 0, ldp, np / 64, st);
         cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (r > 0) total += ms;
