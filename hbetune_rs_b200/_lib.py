@@ -47,6 +47,8 @@ PROTOTYPES = {
     "hbegp_pick_best_run": (C.c_int, [C.c_int, C.POINTER(RunResult)]),
     "hbegp_model_create": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_void_p, C.c_void_p]),
+    "hbegp_model_extend": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_void_p,
+                                     C.c_void_p, C.POINTER(C.c_int)]),
     "hbegp_model_destroy": (C.c_int, [C.c_void_p]),
     "hbegp_model_n": (C.c_long, [C.c_void_p]),
     "hbegp_model_dim": (C.c_int, [C.c_void_p]),

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -44,25 +45,80 @@ static int fail(int code, const std::string& msg) {
         }                                                                                                \
     } while (0)
 
+static inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static const bool g_trace_model = getenv("HBEGP_TRACE_MODEL") != nullptr;  // phase times of model creation on stderr
+
 static inline int round_up(long v, int m) { return (int)(((v + m - 1) / m) * m); }
 
 // dynamic shared memory the d-dependent kernels may use (opt-in limit on sm_100a is 227 KB)
 constexpr size_t kMaxFeatureSmem = 200 * 1024;
 
+// Device buffers of dropped models, kept by their context for the next model.  The tuner replaces its model every
+// generation; cudaMalloc / cudaFree of the n x n factor and the prediction scratch cost 5-80 ms per model (measured
+// at n = 4096..6144), several times the evaluation that fills them.
+struct BufPool {
+    struct Item {
+        void* p;
+        size_t bytes;
+    };
+    std::vector<Item> items;
+    size_t held = 0;
+    static constexpr size_t kMaxItems = 24;
+    static constexpr size_t kMaxHeld = (size_t)16 << 30;
+    void* get(size_t need, size_t* got) {
+        int best = -1;
+        for (int i = 0; i < (int)items.size(); i++)
+            if (items[i].bytes >= need && items[i].bytes <= 2 * need + (1 << 20) && (best < 0 || items[i].bytes < items[best].bytes))
+                best = i;
+        if (best < 0) return nullptr;
+        void* p = items[best].p;
+        *got = items[best].bytes;
+        held -= items[best].bytes;
+        items.erase(items.begin() + best);
+        return p;
+    }
+    void put(void* p, size_t bytes) {
+        if (items.size() >= kMaxItems || held + bytes > kMaxHeld) {
+            cudaFree(p);
+            return;
+        }
+        items.push_back({p, bytes});
+        held += bytes;
+    }
+    void clear() {
+        for (auto& it : items) cudaFree(it.p);
+        items.clear();
+        held = 0;
+    }
+    ~BufPool() { clear(); }
+};
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    BufPool* pool = nullptr;  // optional: where released memory goes and new memory is looked for first
     int ensure(size_t need) {
         if (need <= bytes) return HBEGP_OK;
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-        CUDA_TRY(cudaMalloc(&p, need));
+        release();
+        if (pool && (p = pool->get(need, &bytes))) return HBEGP_OK;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e != cudaSuccess && pool && !pool->items.empty()) {  // out of memory with memory parked in the pool
+            cudaGetLastError();
+            pool->clear();
+            e = cudaMalloc(&p, need);
+        }
+        if (e != cudaSuccess) p = nullptr;
+        CUDA_TRY(e);
         bytes = need;
         return HBEGP_OK;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            if (pool) pool->put(p, bytes);
+            else cudaFree(p);
+        }
         p = nullptr;
         bytes = 0;
     }
@@ -89,12 +145,14 @@ struct EngineBase {
     size_t ws_limit = 0;
     long long launches = 0;
     std::vector<Model*> models;  // live models of this context (orphaned, not leaked, on ctx_destroy)
+    BufPool model_pool;          // buffers of destroyed models (see BufPool)
     virtual ~EngineBase() {}
     virtual int set_data(long n, int d, const void* x, const void* y, bool on_device) = 0;
     virtual int eval_batch(double nu, int B, const double* theta, const double* lo, const double* hi, double* lml,
                            double* grad, int* status) = 0;
     virtual int model_create(double nu, const double* theta, const double* lo, const double* hi, Model** out,
                              double* lml, void* alpha_out, void* kinv_out) = 0;
+    virtual int model_extend(Model* prior, Model** out, double* lml, void* alpha_out, void* kinv_out, int* appended) = 0;
     virtual int debug_factor(double nu, const double* theta, void* k, void* w, void* kinv, int* status) = 0;
     virtual int bench_phase(double nu, int B, const double* theta, int phase, int reps, float* ms_out) = 0;
 };
@@ -106,9 +164,11 @@ struct Model {
     int d = 0, np = 0, nu2 = 5;
     double c = 1.0;
     DevBuf W, alpha, xsT, ls;  // inverse Cholesky factor (np x np), alpha (np), scaled X^T (d x np), length scales
+    DevBuf ldp;                // sum of ln L_ii per 64-row leaf (kept for model_extend)
+    std::vector<double> prm_h; // [noise, c, l_1..l_d] as evaluated (after clamping), in the data type's precision
     DevBuf kstar, part, pmean, nbelow, xs_tmp, mean_tmp, var_tmp;
     void release_all() {
-        W.release(); alpha.release(); xsT.release(); ls.release();
+        W.release(); alpha.release(); xsT.release(); ls.release(); ldp.release();
         kstar.release(); part.release(); pmean.release(); nbelow.release(); xs_tmp.release(); mean_tmp.release(); var_tmp.release();
         acq1.release(); acq2.release(); argv.release(); argi.release();
     }
@@ -121,6 +181,11 @@ struct Model {
     virtual int predict_acquisition(int mode, const hbegp_ynorm* yn, long m, const void* xs, double param, void* out1,
                                     void* out2, long* best, long* n_below) = 0;
     DevBuf acq1, acq2, argv, argi;
+    void use_pool(BufPool* pl) {
+        for (DevBuf* b : {&W, &alpha, &xsT, &ls, &ldp, &kstar, &part, &pmean, &nbelow, &xs_tmp, &mean_tmp, &var_tmp, &acq1, &acq2,
+                          &argv, &argi})
+            b->pool = pl;
+    }
 };
 
 static int nu_to_nu2(double nu, int* nu2) {
@@ -215,18 +280,17 @@ struct Engine : EngineBase {
         if (n <= 0) return fail(HBEGP_ERR_INVALID, "no training data: call hbegp_set_data first");
         if (want <= cap) return HBEGP_OK;
         size_t limit = ws_limit;
-        if (limit == 0) {
-            size_t fr = 0, tot = 0;
-            CUDA_TRY(cudaMemGetInfo(&fr, &tot));
-            // memory already held by the current workspaces is reusable
-            size_t held = A.bytes + W.bytes + gpart.bytes + tpart.bytes + xsT.bytes;
-            limit = (size_t)((double)(fr + held) * 0.7);
-        }
+        size_t fr = 0, tot = 0;
+        CUDA_TRY(cudaMemGetInfo(&fr, &tot));
+        // memory already held by the current workspaces (and parked in the model pool) is reusable
+        const size_t held = A.bytes + W.bytes + gpart.bytes + tpart.bytes + xsT.bytes;
+        if (limit == 0) limit = (size_t)((double)(fr + held + model_pool.held) * 0.7);
         size_t per = per_slot_bytes();
         int fit = (int)std::min<size_t>(limit / per, 4096);
         if (fit < 1) return fail(HBEGP_ERR_NOMEM, "workspace limit too small for one n x n evaluation");
         int newcap = std::min(want, fit);
         if (newcap <= cap) return HBEGP_OK;
+        if ((size_t)newcap * per > fr + held) model_pool.clear();
         drop_graphs();  // buffers may move
         int rc;
         size_t c = (size_t)newcap;
@@ -241,7 +305,7 @@ struct Engine : EngineBase {
         if ((rc = gpart.ensure(c * ntiles_lower() * p() * sizeof(double)))) return rc;
         if ((rc = d_lml.ensure(c * sizeof(double)))) return rc;
         if ((rc = d_grad.ensure(c * p() * sizeof(double)))) return rc;
-        if ((rc = d_status.ensure(c * sizeof(int)))) return rc;
+        if ((rc = d_status.ensure(((size_t)c + 1) * sizeof(int)))) return rc;  // + the prefix check of model_extend
         if (h_prm_bytes < c * p() * sizeof(T)) {
             if (h_prm) cudaFreeHost(h_prm);
             h_prm_bytes = c * p() * sizeof(T);
@@ -295,6 +359,15 @@ struct Engine : EngineBase {
         const int s1 = q1 * TILE, s2 = s - s1;
         int rc;
         if ((rc = chol_inv(st, s0, cnt, r0, s1, sd))) return rc;
+        return merge_node(st, s0, cnt, r0, s1, s2, sd);
+    }
+
+    // One node of the recursion with the (1,1) block already done: W11 = L11^-1 is in W, the rows below hold A21 and
+    // A22.  Also the whole of an append (model_extend): W11 comes from the prior model, s2 covers the new rows.
+    int merge_node(cudaStream_t st, int s0, int cnt, int r0, int s1, int s2, Side sd) {
+        T* Ab = (T*)A.p + (size_t)s0 * mstride();
+        T* Wb = (T*)W.p + (size_t)s0 * mstride();
+        int rc;
         T* A21 = Ab + (long)(r0 + s1) * np + r0;
         T* W21 = Wb + (long)(r0 + s1) * np + r0;
         T* W11 = Wb + (long)r0 * np + r0;
@@ -362,7 +435,7 @@ struct Engine : EngineBase {
         const size_t xsm = 2 * (size_t)d * TILE * sizeof(T);
         k_scale_x<T><<<dim3((np + 255) / 256, d, cnt), 256, 0, st>>>((const T*)dX.p, (int)n, d, np, pr, p(), xs);
         launches++;
-        k_assemble<T, NU2><<<dim3(ntiles_lower(), 1, cnt), 256, xsm, st>>>(xs, (int)n, d, np, pr, p(), Ab, mstride());
+        k_assemble<T, NU2><<<dim3(ntiles_lower(), 1, cnt), 256, xsm, st>>>(xs, (int)n, d, np, pr, p(), Ab, mstride(), 0);
         launches++;
         CUDA_TRY(cudaGetLastError());
         if (phase < 1) return HBEGP_OK;
@@ -517,6 +590,10 @@ struct Engine : EngineBase {
         return HBEGP_OK;
     }
 
+    int model_extend(Model* prior, Model** out, double* lml, void* alpha_out, void* kinv_out, int* appended) override;
+    template <int NU2>
+    int append_nu(ModelT<T>* prior, int r1, bool want_kinv);
+    int finish_model(int nu2, Model** out, double* lml, void* alpha_out, void* kinv_out);
     int model_create(double nu, const double* theta, const double* lo, const double* hi, Model** out, double* lml,
                      void* alpha_out, void* kinv_out) override;
 
@@ -570,9 +647,9 @@ struct Engine : EngineBase {
             return HBEGP_OK;
         };
         k_scale_x<T><<<dim3((np + 255) / 256, d, 1), 256, 0, stream>>>((const T*)dX.p, (int)n, d, np, (T*)prm.p, p(), (T*)xsT.p);
-        if (nu2 == 5) k_assemble<T, 5><<<dim3(ntiles_lower(), 1, 1), 256, xsm, stream>>>((T*)xsT.p, (int)n, d, np, (T*)prm.p, p(), (T*)A.p, mstride());
-        else if (nu2 == 3) k_assemble<T, 3><<<dim3(ntiles_lower(), 1, 1), 256, xsm, stream>>>((T*)xsT.p, (int)n, d, np, (T*)prm.p, p(), (T*)A.p, mstride());
-        else k_assemble<T, 1><<<dim3(ntiles_lower(), 1, 1), 256, xsm, stream>>>((T*)xsT.p, (int)n, d, np, (T*)prm.p, p(), (T*)A.p, mstride());
+        if (nu2 == 5) k_assemble<T, 5><<<dim3(ntiles_lower(), 1, 1), 256, xsm, stream>>>((T*)xsT.p, (int)n, d, np, (T*)prm.p, p(), (T*)A.p, mstride(), 0);
+        else if (nu2 == 3) k_assemble<T, 3><<<dim3(ntiles_lower(), 1, 1), 256, xsm, stream>>>((T*)xsT.p, (int)n, d, np, (T*)prm.p, p(), (T*)A.p, mstride(), 0);
+        else k_assemble<T, 1><<<dim3(ntiles_lower(), 1, 1), 256, xsm, stream>>>((T*)xsT.p, (int)n, d, np, (T*)prm.p, p(), (T*)A.p, mstride(), 0);
         CUDA_TRY(cudaGetLastError());
         if (k && (rc = copy_out((T*)A.p, k, 1))) { tmp.release(); return rc; }
         if ((rc = chol_inv(stream, 0, 1, 0, np))) { tmp.release(); return rc; }
@@ -798,28 +875,43 @@ int Engine<T>::model_create(double nu, const double* theta, const double* lo, co
     if ((rc = ensure_capacity(1))) return rc;
     fill_params(theta, lo, hi, h_prm);
     const bool want_kinv = kinv_out != nullptr;
+    const double t0 = now_ms();
     if ((rc = run_chunk(nu2, 1, false, want_kinv))) return rc;
+    if (g_trace_model) fprintf(stderr, "[hbegp] model_create: evaluation %.3f ms\n", now_ms() - t0);
+    return finish_model(nu2, out, lml, alpha_out, kinv_out);
+}
+
+// Moves the evaluation in batch slot 0 into a model object (fit.rs:166-175 / :56-67).
+template <typename T>
+int Engine<T>::finish_model(int nu2, Model** out, double* lml, void* alpha_out, void* kinv_out) {
+    int rc;
     if (h_status[0] != 0 || !std::isfinite(h_out[0]))
         return fail(HBEGP_NOT_PD, "Kernel matrix must be invertible. (fit.rs:55)");
     if (lml) *lml = h_out[0];
+    const double t0 = now_ms();
     ModelT<T>* m = new ModelT<T>();
     m->eng = this;
+    m->use_pool(&model_pool);
     m->dtype = dtype;
     m->n = n;
     m->d = d;
     m->np = np;
     m->nu2 = nu2;
     m->c = (double)h_prm[1];
+    m->prm_h.assign(h_prm, h_prm + p());
     auto bail = [&](int code) { delete m; return code; };
     if ((rc = m->W.ensure((size_t)np * np * sizeof(T)))) return bail(rc);
     if ((rc = m->alpha.ensure((size_t)np * sizeof(T)))) return bail(rc);
     if ((rc = m->xsT.ensure((size_t)d * np * sizeof(T)))) return bail(rc);
     if ((rc = m->ls.ensure((size_t)d * sizeof(T)))) return bail(rc);
+    if ((rc = m->ldp.ensure((size_t)(np / TILE) * sizeof(T)))) return bail(rc);
+    const double t1 = now_ms();
     cudaError_t ce;
     ce = cudaMemcpyAsync(m->W.p, W.p, (size_t)np * np * sizeof(T), cudaMemcpyDeviceToDevice, stream);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(m->alpha.p, alpha.p, (size_t)np * sizeof(T), cudaMemcpyDeviceToDevice, stream);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(m->xsT.p, xsT.p, (size_t)d * np * sizeof(T), cudaMemcpyDeviceToDevice, stream);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(m->ls.p, (T*)prm.p + 2, (size_t)d * sizeof(T), cudaMemcpyDeviceToDevice, stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(m->ldp.p, ldp.p, (size_t)(np / TILE) * sizeof(T), cudaMemcpyDeviceToDevice, stream);
     if (ce == cudaSuccess && alpha_out) ce = cudaMemcpyAsync(alpha_out, alpha.p, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, stream);
     if (ce != cudaSuccess) { delete m; return fail(HBEGP_ERR_CUDA, std::string("model_create copy: ") + cudaGetErrorString(ce)); }
     if (kinv_out) {
@@ -835,9 +927,98 @@ int Engine<T>::model_create(double nu, const double* theta, const double* lo, co
     }
     ce = cudaStreamSynchronize(stream);
     if (ce != cudaSuccess) { delete m; return fail(HBEGP_ERR_CUDA, std::string("model_create: ") + cudaGetErrorString(ce)); }
+    if (g_trace_model) fprintf(stderr, "[hbegp] finish_model: buffers %.3f ms, copies %.3f ms\n", t1 - t0, now_ms() - t1);
     models.push_back(m);
     *out = m;
     return HBEGP_OK;
+}
+
+// Append path of `extend`.  The prior model's W11 = L11^-1 over its first r1 rows stays valid
+// when those rows are an unchanged prefix of the new data and theta is unchanged, so only the new tile rows are
+// assembled and the factorisation is one node of the recursion: O(n^2 k) instead of O(n^3) for k new rows.
+template <typename T>
+template <int NU2>
+int Engine<T>::append_nu(ModelT<T>* prior, int r1, bool want_kinv) {
+    cudaStream_t st = stream;
+    T* Ab = (T*)A.p;
+    T* Wb = (T*)W.p;
+    T* xs = (T*)xsT.p;
+    T* pr = (T*)prm.p;
+    const int q = r1 / TILE, tile0 = q * (q + 1) / 2;
+    const size_t xsm = 2 * (size_t)d * TILE * sizeof(T);
+    if (ntiles_lower() > tile0) {
+        k_assemble<T, NU2><<<dim3(ntiles_lower() - tile0, 1, 1), 256, xsm, st>>>(xs, (int)n, d, np, pr, p(), Ab, mstride(), tile0);
+        launches++;
+    }
+    CUDA_TRY(cudaMemcpy2DAsync(Wb, (size_t)np * sizeof(T), prior->W.p, (size_t)prior->np * sizeof(T), (size_t)r1 * sizeof(T), r1,
+                               cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ldp.p, prior->ldp.p, (size_t)q * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    int rc;
+    if (np > r1 && (rc = merge_node(st, 0, 1, 0, r1, np - r1, Side()))) return rc;
+    k_trmv_lower<T><<<dim3(np / 8, 1, 1), 256, 0, st>>>(Wb, mstride(), np, (const T*)dY.p, 0, (T*)u.p, np);
+    launches++;
+    k_trmv_lower_t_part<T><<<dim3(np / TILE, nchunks(), 1), 256, 0, st>>>(Wb, mstride(), np, (T*)u.p, np, (T*)tpart.p, nchunks());
+    launches++;
+    k_sum_chunks<T><<<dim3((np + 255) / 256, 1, 1), 256, 0, st>>>((T*)tpart.p, nchunks(), np, (T*)alpha.p, np);
+    launches++;
+    if (want_kinv && (rc = lauum(st, Ab, Wb, 1))) return rc;
+    k_finish<T><<<1, 256, 0, st>>>((const T*)dY.p, (T*)alpha.p, np, (int)n, np, (T*)ldp.p, np / TILE, (double*)gpart.p,
+                                  (long)ntiles_lower() * p(), ntiles_lower(), p(), (int*)d_status.p, (double*)d_lml.p,
+                                  (double*)d_grad.p, 0);
+    launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h_out, d_lml.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_status, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return HBEGP_OK;
+}
+
+// FittedKernel::extend (fit.rs:33-68): the prior model's theta on the context's current data, one evaluation.
+template <typename T>
+int Engine<T>::model_extend(Model* prior_, Model** out, double* lml, void* alpha_out, void* kinv_out, int* appended) {
+    if (!prior_ || !out) return fail(HBEGP_ERR_INVALID, "model_extend: bad arguments");
+    *out = nullptr;
+    if (appended) *appended = 0;
+    ModelT<T>* prior = static_cast<ModelT<T>*>(prior_);
+    if (prior->eng != this) return fail(HBEGP_ERR_INVALID, "model_extend: the prior model belongs to another (or a destroyed) context");
+    if (n <= 0) return fail(HBEGP_ERR_INVALID, "model_extend: no training data (hbegp_set_data)");
+    if (prior->d != d) return fail(HBEGP_ERR_INVALID, "model_extend: the data has a different number of features than the prior model");
+    if ((int)prior->prm_h.size() != p()) return fail(HBEGP_ERR_INVALID, "model_extend: prior model without parameters");
+    int rc;
+    const double t_start = now_ms();
+    CUDA_TRY(cudaSetDevice(device));
+    if ((rc = ensure_capacity(1))) return rc;
+    for (int k = 0; k < p(); k++) h_prm[k] = (T)prior->prm_h[k];
+    const int nu2 = prior->nu2;
+    const bool want_kinv = kinv_out != nullptr;
+    // the append needs at least one complete 64-row leaf of the prior model and the old rows as a prefix
+    int r1 = (int)(std::min<long>(prior->n, n) / TILE) * TILE;
+    if (prior->n > n) r1 = 0;
+    if (r1 > 0) {
+        CUDA_TRY(cudaMemcpyAsync(prm.p, h_prm, (size_t)p() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemsetAsync(d_status.p, 0, sizeof(int), stream));
+        CUDA_TRY(cudaMemsetAsync((int*)d_status.p + cap, 0, sizeof(int), stream));
+        k_scale_x<T><<<dim3((np + 255) / 256, d, 1), 256, 0, stream>>>((const T*)dX.p, (int)n, d, np, (T*)prm.p, p(), (T*)xsT.p);
+        launches++;
+        k_prefix_mismatch<T><<<dim3((r1 + 255) / 256, d), 256, 0, stream>>>((const T*)xsT.p, np, (const T*)prior->xsT.p, prior->np, d, r1,
+                                                                          (int*)d_status.p + cap);
+        launches++;
+        int mismatch = 1;
+        CUDA_TRY(cudaMemcpyAsync(&mismatch, (int*)d_status.p + cap, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (mismatch) r1 = 0;
+    }
+    if (r1 == 0) {  // different rows or row order: the full evaluation
+        if ((rc = run_chunk(nu2, 1, false, want_kinv))) return rc;
+    } else {
+        if (nu2 == 5) rc = append_nu<5>(prior, r1, want_kinv);
+        else if (nu2 == 3) rc = append_nu<3>(prior, r1, want_kinv);
+        else rc = append_nu<1>(prior, r1, want_kinv);
+        if (rc) return rc;
+        if (appended) *appended = 1;
+    }
+    if (g_trace_model) fprintf(stderr, "[hbegp] model_extend: %s %.3f ms\n", r1 ? "append" : "full evaluation", now_ms() - t_start);
+    return finish_model(nu2, out, lml, alpha_out, kinv_out);
 }
 
 // cudaFuncSetAttribute for every GEMM instantiation up front (never inside a stream capture)
@@ -1055,6 +1236,7 @@ int hbegp_ctx_destroy(hbegp_ctx* ctx) {
     cudaStreamSynchronize(e->stream);
     for (Model* m : e->models) {  // models outliving their context keep answering with HBEGP_ERR_INVALID
         m->release_all();
+        m->use_pool(nullptr);
         m->eng = nullptr;
     }
     e->models.clear();
@@ -1118,6 +1300,17 @@ int hbegp_model_create(hbegp_ctx* ctx, double nu, const double* theta, const dou
     Model* m = nullptr;
     int rc = ctx->eng->model_create(nu, theta, lo, hi, &m, lml, alpha_out, kinv_out);
     *out = nullptr;
+    if (rc) return rc;
+    *out = new hbegp_model{m};
+    return HBEGP_OK;
+}
+
+int hbegp_model_extend(hbegp_ctx* ctx, hbegp_model* prior, hbegp_model** out, double* lml, void* alpha_out, void* kinv_out,
+                       int* appended) {
+    if (!ctx || !prior || !prior->m || !out) return fail(HBEGP_ERR_INVALID, "hbegp_model_extend: bad arguments");
+    Model* m = nullptr;
+    *out = nullptr;
+    int rc = ctx->eng->model_extend(prior->m, &m, lml, alpha_out, kinv_out, appended);
     if (rc) return rc;
     *out = new hbegp_model{m};
     return HBEGP_OK;

@@ -65,16 +65,27 @@ __global__ void k_scale_x(const T* __restrict__ x, int n, int d, int np, const T
     xsT[((long)b * d + k) * np + i] = v;
 }
 
+// Number of scaled training inputs that differ between two models' X^T buffers (first `cols` points): an
+// append (model_extend) is only valid when the old rows are an unchanged prefix of the new data.
+template <typename T>
+__global__ void k_prefix_mismatch(const T* __restrict__ a, int lda, const T* __restrict__ b, int ldb, int d, int cols,
+                                  int* __restrict__ count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = blockIdx.y;
+    if (i >= cols) return;
+    if (!(a[(long)k * lda + i] == b[(long)k * ldb + i])) atomicAdd(count, 1);
+}
+
 // K = c * matern(|xs_i - xs_j|) + noise * I on the lower tiles (diagonal tiles written in full).
 template <typename T, int NU2>
 __global__ void __launch_bounds__(256) k_assemble(const T* __restrict__ xsT, int n, int d, int np,
                                                   const T* __restrict__ prm, int pstride, T* __restrict__ K,
-                                                  long kstride) {
+                                                  long kstride, int tile0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* xi = reinterpret_cast<T*>(smem_raw);  // [d][64]
     T* xj = xi + d * TILE;
     int mt, nt;
-    lower_tile(blockIdx.x, mt, nt);
+    lower_tile(blockIdx.x + tile0, mt, nt);  // tile0 > 0: only the tile rows an append adds (model_extend)
     const int b = blockIdx.z;
     const int i0 = mt * TILE, j0 = nt * TILE;
     const T* xb = xsT + (long)b * d * np;

@@ -268,5 +268,5 @@ class EstimatorGPR:
         x = np.ascontiguousarray(x, dtype=self.A)
         assert len(y) == x.shape[0]
         y_train, y_norm = YNormalize.new_project_into_normalized(y, self._y_projection, self._known_optimum, self.A)
-        fk = FittedKernel.extend(self.ctx, prior.kernel, x, y_train, prior.noise, want_kinv=want_kinv)
+        fk = FittedKernel.extend(self.ctx, prior.kernel, x, y_train, prior.noise, want_kinv=want_kinv, prior=prior.fitted)
         return SurrogateModelGPR(fk, x, y_train, y_norm, self.A)

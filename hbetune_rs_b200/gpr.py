@@ -234,20 +234,31 @@ class Context:
 class Model:
     """A fitted model resident on the GPU (``hbegp_model``): X, alpha and L^-1 stay in HBM."""
 
-    def __init__(self, ctx: Context, theta, nu=2.5, lo=None, hi=None, want_alpha=True, want_kinv=False):
-        theta = np.ascontiguousarray(theta, dtype=np.float64)
-        lo = None if lo is None else np.ascontiguousarray(lo, dtype=np.float64)
-        hi = None if hi is None else np.ascontiguousarray(hi, dtype=np.float64)
+    def __init__(self, ctx: Context, theta=None, nu=2.5, lo=None, hi=None, want_alpha=True, want_kinv=False,
+                 prior: Optional["Model"] = None):
         self.ctx, self.A = ctx, ctx.A
         self.alpha = np.empty(ctx.n, dtype=self.A) if want_alpha else None
         self.k_inv = np.empty((ctx.n, ctx.n), dtype=self.A) if want_kinv else None
         h = C.c_void_p()
         lml = C.c_double()
-        rc = lib.hbegp_model_create(ctx._h, nu, _ptr(theta), _ptr(lo), _ptr(hi), C.byref(h), C.byref(lml),
-                                    _ptr(self.alpha), _ptr(self.k_inv))
+        self.appended = False
+        if prior is not None:
+            # hbegp_model_extend: the prior's parameters on the context's current data (block append when possible)
+            appended = C.c_int(0)
+            rc = lib.hbegp_model_extend(ctx._h, prior._h, C.byref(h), C.byref(lml), _ptr(self.alpha), _ptr(self.k_inv),
+                                        C.byref(appended))
+            what = "hbegp_model_extend"
+            self.appended = bool(appended.value)
+        else:
+            theta = np.ascontiguousarray(theta, dtype=np.float64)
+            lo = None if lo is None else np.ascontiguousarray(lo, dtype=np.float64)
+            hi = None if hi is None else np.ascontiguousarray(hi, dtype=np.float64)
+            rc = lib.hbegp_model_create(ctx._h, nu, _ptr(theta), _ptr(lo), _ptr(hi), C.byref(h), C.byref(lml),
+                                        _ptr(self.alpha), _ptr(self.k_inv))
+            what = "hbegp_model_create"
         if rc == _lib.NOT_PD:
             raise np.linalg.LinAlgError("Kernel matrix must be invertible.")  # fit.rs:55 panics here
-        check(rc, "hbegp_model_create")
+        check(rc, what)
         self._h = h
         self.lml = lml.value
         self.n, self.d = ctx.n, ctx.d
@@ -325,12 +336,22 @@ class FittedKernel:
 
     @classmethod
     def extend(cls, ctx: Context, kernel: Product, x_train, y_train, noise: BoundedValue,
-               want_kinv: bool = False) -> "FittedKernel":
-        """``FittedKernel::extend`` (``src/gpr/fit.rs:33-68``): one evaluation, no optimisation."""
+               want_kinv: bool = False, prior: Optional["FittedKernel"] = None) -> "FittedKernel":
+        """``FittedKernel::extend`` (``src/gpr/fit.rs:33-68``): one evaluation, no optimisation.
+
+        With ``prior`` (the fitted kernel being extended, i.e. the reference's ``self``) whose model is still
+        resident on ``ctx``, the library appends the new rows to the prior factorisation when the old rows are an
+        unchanged prefix of ``x_train`` (``hbegp_model_extend``) instead of refactorising everything."""
         ctx.set_data(x_train, y_train)
         theta = np.array([math.log(noise.value)] + kernel.theta())
         try:
-            model = ctx.model(theta, kernel.k2.nu, None, None, want_alpha=True, want_kinv=want_kinv)
+            pm = getattr(prior, "model", None)
+            if (pm is not None and getattr(pm, "_h", None) and pm.ctx is ctx
+                    and prior.noise.value == noise.value and prior.kernel.theta() == kernel.theta()
+                    and prior.kernel.k2.nu == kernel.k2.nu):
+                model = Model(ctx, want_alpha=True, want_kinv=want_kinv, prior=pm)
+            else:
+                model = ctx.model(theta, kernel.k2.nu, None, None, want_alpha=True, want_kinv=want_kinv)
         except np.linalg.LinAlgError:
             raise RuntimeError("Kernel matrix must be invertible.")
         return cls(kernel, noise, model.alpha, model.k_inv, model.lml, model, 1)

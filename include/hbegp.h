@@ -100,6 +100,15 @@ int hbegp_pick_best_run(int n_runs, const hbegp_run_result* results);
  * (the reference panics there, fit.rs:55). */
 int hbegp_model_create(hbegp_ctx* ctx, double nu, const double* theta, const double* lo, const double* hi,
                        hbegp_model** out, double* lml, void* alpha_out, void* kinv_out);
+/* FittedKernel::extend (src/gpr/fit.rs:33-68) from a prior model: the prior's kernel and noise (as evaluated)
+ * on the context's CURRENT data (hbegp_set_data), one evaluation, no optimisation.  Outputs as for
+ * hbegp_model_create.  When the prior's training rows are an unchanged prefix of the new data -- the one
+ * in-tree call site appends the validation samples to the evaluation history, minimize.rs:629-644 -- only the
+ * added rows are factorised (an O(n^2 k) block append, checked on the device; the result is the same model up to
+ * rounding); otherwise this is the full evaluation.  *appended (may be NULL) reports which: 1 append, 0 full.
+ * The prior stays valid and must belong to `ctx`. */
+int hbegp_model_extend(hbegp_ctx* ctx, hbegp_model* prior, hbegp_model** out, double* lml, void* alpha_out,
+                       void* kinv_out, int* appended);
 int hbegp_model_destroy(hbegp_model* model);
 long hbegp_model_n(const hbegp_model* model);
 int hbegp_model_dim(const hbegp_model* model);

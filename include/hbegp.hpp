@@ -179,6 +179,19 @@ struct FittedKernel {
         return finish(ctx, kernel, noise, theta.data(), nullptr, nullptr, n, 1);
     }
 
+    // FittedKernel::extend as the reference spells it -- `self` is the fitted kernel being extended.  The library
+    // appends to the prior factorisation when the old rows are an unchanged prefix of x (hbegp_model_extend).
+    FittedKernel extend(Context& ctx, const std::vector<A>& x, long n, int d, const std::vector<A>& y, bool* appended = nullptr) const {
+        check(hbegp_set_data(ctx.get(), n, d, x.data(), y.data()), "hbegp_set_data");
+        FittedKernel fk{kernel, noise, std::vector<A>(n), 0.0, std::make_shared<ModelHandle>(), 1};
+        int app = 0;
+        int rc = hbegp_model_extend(ctx.get(), model->h, &fk.model->h, &fk.lml, fk.alpha.data(), nullptr, &app);
+        if (rc == HBEGP_NOT_PD) throw std::runtime_error("Kernel matrix must be invertible.");  // fit.rs:55
+        check(rc, "hbegp_model_extend");
+        if (appended) *appended = app != 0;
+        return fk;
+    }
+
 private:
     static FittedKernel finish(Context& ctx, const Product& kernel, const BoundedValue& noise, const double* theta, const double* lo,
                                const double* hi, long n, long evals) {
@@ -328,7 +341,7 @@ public:
                                 const SurrogateModelGPR<A>& prior) const {
         const int d = (int)length_scale_bounds_.size();
         auto yn = YNormalize<A>::new_project_into_normalized(y, y_projection_, has_ko_ ? &ko_ : nullptr);
-        auto fk = FittedKernel<A>::extend(ctx, prior.kernel(), x, n, d, yn.first, prior.noise());
+        auto fk = prior.fitted().extend(ctx, x, n, d, yn.first);
         return SurrogateModelGPR<A>(std::move(fk), yn.second, d);
     }
 

@@ -233,8 +233,20 @@ impl<A: Scalar> Estimator<A> for EstimatorGPRCuda {
             ffi::hbegp_set_data((self.ctx).0, n as c_long, d as c_int, x.as_ptr() as *const c_void,
                                 y_train.as_ptr() as *const c_void)
         });
-        let mut theta = vec![prior.noise.value().ln()];
-        theta.extend(prior.kernel.theta());
-        Ok(self.finish(prior.kernel.clone(), prior.noise.clone(), &theta, None, y_norm, d))
+        // hbegp_model_extend takes theta from the prior's device model and appends the new rows to its
+        // factorisation when the old rows are an unchanged prefix of x (minimize.rs:629-644 chains the validation
+        // samples behind the evaluation history); otherwise it runs the full evaluation.
+        let mut model = std::ptr::null_mut();
+        let mut lml = 0.0;
+        let rc = unsafe {
+            ffi::hbegp_model_extend((self.ctx).0, prior.device.0, &mut model, &mut lml, std::ptr::null_mut(),
+                                    std::ptr::null_mut(), std::ptr::null_mut())
+        };
+        assert!(rc != ffi::HBEGP_NOT_PD, "Kernel matrix must be invertible."); // fit.rs:55
+        check(rc);
+        Ok(SurrogateModelCuda {
+            kernel: prior.kernel.clone(), noise: prior.noise.clone(), y_norm, lml, n_features: d,
+            device: Rc::new(DeviceModel(model)),
+        })
     }
 }

@@ -75,6 +75,10 @@ extern "C" {
         ctx: *mut hbegp_ctx, nu: c_double, theta: *const c_double, lo: *const c_double, hi: *const c_double,
         out: *mut *mut hbegp_model, lml: *mut c_double, alpha_out: *mut c_void, kinv_out: *mut c_void,
     ) -> c_int;
+    pub fn hbegp_model_extend(
+        ctx: *mut hbegp_ctx, prior: *mut hbegp_model, out: *mut *mut hbegp_model, lml: *mut c_double,
+        alpha_out: *mut c_void, kinv_out: *mut c_void, appended: *mut c_int,
+    ) -> c_int;
     pub fn hbegp_model_destroy(model: *mut hbegp_model) -> c_int;
     pub fn hbegp_model_n(model: *const hbegp_model) -> c_long;
     pub fn hbegp_model_dim(model: *const hbegp_model) -> c_int;

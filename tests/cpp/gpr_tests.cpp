@@ -149,6 +149,46 @@ static int run_all() {
         EXPECT_CLOSE(one.second, r.second[best], 1e-12);
     });
 
+    // fit.rs:33-68 through hbegp_model_extend: history + validation samples (minimize.rs:629-644) is a block append
+    run("extend_appends_to_the_prior_factorisation", [&] {
+        RNG rng = RNG::new_with_seed(99);
+        const long n = 150, extra = 6;
+        std::vector<double> xs, ys;
+        for (long i = 0; i < n + extra; i++) {
+            const double a = rng.uniform(0.0, 1.0), b = rng.uniform(0.0, 1.0);
+            xs.push_back(a);
+            xs.push_back(b);
+            ys.push_back(30.0 * ((a - 0.4) * (a - 0.4) + (b - 0.4) * (b - 0.4)) + 5.0 + 0.2 * rng.uniform(-1.0, 1.0));
+        }
+        EstimatorGPR est(2);
+        est.noise_bounds(1e-2, 1e1).n_restarts_optimizer(1);
+        std::vector<double> x0(xs.begin(), xs.begin() + 2 * n), y0(ys.begin(), ys.begin() + n);
+        auto prior = est.estimate<double>(ctx, x0, n, y0, nullptr, rng);
+        auto yn = YNormalize<double>::new_project_into_normalized(ys, Projection::Linear, nullptr);
+        bool appended = false;
+        auto app = prior.fitted().extend(ctx, xs, n + extra, 2, yn.first, &appended);
+        EXPECT(appended, "history + new rows must take the append path");
+        auto full = FittedKernel<double>::extend(ctx, prior.kernel(), xs, n + extra, 2, yn.first, prior.noise());
+        EXPECT_CLOSE(app.lml, full.lml, 1e-9 * std::fabs(full.lml));
+        std::vector<double> cand;
+        for (int i = 0; i < 40; i++) cand.push_back(rng.uniform(0.0, 1.0));
+        std::vector<double> v1, v2;
+        auto m1 = predict(app, cand, 20, &v1), m2 = predict(full, cand, 20, &v2);
+        for (int i = 0; i < 20; i++) {
+            EXPECT_CLOSE(m1[i], m2[i], 1e-9);
+            EXPECT_CLOSE(v1[i], v2[i], 1e-9);
+        }
+        // rows in another order: the full evaluation, same answer as before
+        std::vector<double> xr(xs), yr(yn.first);
+        std::swap(xr[0], xr[2]);
+        std::swap(xr[1], xr[3]);
+        std::swap(yr[0], yr[1]);
+        auto perm = prior.fitted().extend(ctx, xr, n + extra, 2, yr, &appended);
+        EXPECT(!appended, "a permuted history must not take the append path");
+        auto m3 = predict(perm, cand, 20);
+        for (int i = 0; i < 20; i++) EXPECT_CLOSE(m3[i], m2[i], 1e-9);
+    });
+
     run("bounds_errors", [&] {
         std::vector<double> xs{0.1, 0.9}, ys{1.0, 2.0};
         RNG rng = RNG::new_with_seed(1);
