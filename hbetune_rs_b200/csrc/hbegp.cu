@@ -139,6 +139,7 @@ struct EngineBase {
     cudaStream_t main_side = nullptr;
     cudaEvent_t main_a = nullptr, main_b = nullptr;
     bool use_side = true;
+    bool use_node128 = true;
     cudaEvent_t fork_ev = nullptr;
     long n = 0;
     int d = 0, np = 0;
@@ -349,6 +350,13 @@ struct Engine : EngineBase {
         if (s == TILE) {
             k_leaf<T><<<dim3(1, 1, cnt), 256, leaf_smem_bytes<T>(), st>>>(Ab, Wb, mstride(), np, r0, (T*)ldp.p + (size_t)s0 * (np / TILE), np / TILE,
                                                        (int*)d_status.p + s0);
+            launches++;
+            CUDA_TRY(cudaGetLastError());
+            return HBEGP_OK;
+        }
+        if (s == 2 * TILE && use_node128) {  // the bottom node of the tree in one launch
+            k_node128<T><<<dim3(1, 1, cnt), 256, node128_smem_bytes<T>(), st>>>(Ab, Wb, mstride(), np, r0, (T*)ldp.p + (size_t)s0 * (np / TILE),
+                                                                              np / TILE, (int*)d_status.p + s0);
             launches++;
             CUDA_TRY(cudaGetLastError());
             return HBEGP_OK;
@@ -1037,6 +1045,7 @@ static int configure_gemms() {
     // kernels whose dynamic shared memory grows with the feature count d (two d x 64 operand tiles)
     const int big = (int)kMaxFeatureSmem;
     CUDA_TRY(cudaFuncSetAttribute(k_leaf<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem_bytes<T>()));
+    CUDA_TRY(cudaFuncSetAttribute(k_node128<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)node128_smem_bytes<T>()));
     CUDA_TRY(cudaFuncSetAttribute(k_assemble<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(k_assemble<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(k_assemble<T, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -1220,6 +1229,7 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
         return fail(HBEGP_ERR_CUDA, "ctx_create: side stream");
     }
     if (const char* s = getenv("HBEGP_SIDE")) e->use_side = atoi(s) != 0;
+    if (const char* s = getenv("HBEGP_NODE128")) e->use_node128 = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_PAD")) {
         const bool pad = atoi(s) != 0;
         if (dtype == HBEGP_F64) static_cast<Engine<double>*>(e)->pad_batches = pad;

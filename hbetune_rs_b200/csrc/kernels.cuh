@@ -163,28 +163,22 @@ __device__ __forceinline__ double pivot_rcp<double>(double d) {
 //  * inverse: the four 16x16 diagonal blocks are inverted side by side (15 steps instead of 63), the off-diagonal
 //    blocks follow by block forward substitution W_PQ = -W_PP sum_R L_PR W_RQ (three levels of small products).
 template <typename T>
-constexpr size_t leaf_smem_bytes() { return (2 * (size_t)TILE * (TILE + 1) + 2 * TILE) * sizeof(T); }
+__host__ __device__ constexpr size_t leaf_tile_bytes() { return sizeof(T) * TILE * (TILE + 1); }
+template <typename T>
+constexpr size_t leaf_smem_bytes() { return 2 * leaf_tile_bytes<T>() + 2 * TILE * sizeof(T); }
+template <typename T>
+constexpr size_t node128_smem_bytes() { return 5 * leaf_tile_bytes<T>() + 2 * TILE * sizeof(T); }
 
-template <typename T, int DBG = 0>  // DBG: probe-only switch (1: skip the Cholesky loops, 2: skip the inverse)
-__global__ void __launch_bounds__(256) k_leaf(T* __restrict__ A, T* __restrict__ W, long mstride, int np, int r0,
-                                              T* __restrict__ ldp, int ldp_stride, int* __restrict__ status) {
-    extern __shared__ __align__(16) unsigned char leaf_smem_raw[];
-    typedef T Row[TILE + 1];
-    Row* as = reinterpret_cast<Row*>(leaf_smem_raw);                                   // u (lower); scratch (upper)
-    Row* ws = reinterpret_cast<Row*>(leaf_smem_raw + sizeof(T) * TILE * (TILE + 1));   // W = L^-1
-    T* rdv = reinterpret_cast<T*>(leaf_smem_raw + 2 * sizeof(T) * TILE * (TILE + 1)); // 1 / u_jj
-    T* dinv = rdv + TILE;                                                              // 1 / L_jj
-    __shared__ int fail;
-    const int b = blockIdx.z, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    T* Ab = A + (long)b * mstride + (long)r0 * np + r0;
-    T* Wb = W + (long)b * mstride + (long)r0 * np + r0;
-    if (tid == 0) fail = 0;
+// The leaf on shared memory.  In: as = the 64x64 block (lower part, zeros above).  Out: ws = L^-1 (zeros above the
+// diagonal), dinv[i] = 1 / L_ii; *fail = 1 when a pivot is not positive.  Ends with a barrier.  `as` is scratch after.
+template <typename T, int DBG>
+__device__ __forceinline__ void leaf_core(T (*as)[TILE + 1], T (*ws)[TILE + 1], T* rdv, T* dinv, int* fail, int tid) {
+    const int tx = tid & 15, ty = tid >> 4;
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int i = ty + 16 * a, k = tx + 16 * q;
-            as[i][k] = (k <= i) ? Ab[(long)i * np + k] : T(0);
             ws[i][k] = (i == k) ? T(1) : T(0);
         }
     // ---- blocked Cholesky (nb = 16) on unscaled columns
@@ -210,7 +204,7 @@ __global__ void __launch_bounds__(256) k_leaf(T* __restrict__ A, T* __restrict__
 #pragma unroll
                 for (int t = jj >> 2; t < 4; t++) ukj[t] = as[c0 + pq + 4 * t][j];
                 if (!(dj > T(0)) || !(dj <= T(1e300))) {
-                    if (tid == 0) fail = 1;
+                    if (tid == 0) *fail = 1;
                     dj = T(1);
                 }
                 const T rd = pivot_rcp<T>(dj);
@@ -284,6 +278,42 @@ __global__ void __launch_bounds__(256) k_leaf(T* __restrict__ A, T* __restrict__
         }
     }
     __syncthreads();
+}
+
+// sum_i ln L_ii of a leaf (first warp), from dinv
+template <typename T>
+__device__ __forceinline__ void leaf_logdet(const T* dinv, int tid, T* out) {
+    if (tid < 32) {
+        T s = T(0);
+        for (int i = tid; i < TILE; i += 32) s += -dev_log<T>(dinv[i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (tid == 0) *out = s;
+    }
+}
+
+template <typename T, int DBG = 0>  // DBG: probe-only switch (1: skip the Cholesky loops, 2: skip the inverse)
+__global__ void __launch_bounds__(256) k_leaf(T* __restrict__ A, T* __restrict__ W, long mstride, int np, int r0,
+                                              T* __restrict__ ldp, int ldp_stride, int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char leaf_smem_raw[];
+    typedef T Row[TILE + 1];
+    Row* as = reinterpret_cast<Row*>(leaf_smem_raw);                              // u (lower); scratch (upper)
+    Row* ws = reinterpret_cast<Row*>(leaf_smem_raw + leaf_tile_bytes<T>());      // W = L^-1
+    T* rdv = reinterpret_cast<T*>(leaf_smem_raw + 2 * leaf_tile_bytes<T>());     // 1 / u_jj
+    T* dinv = rdv + TILE;                                                         // 1 / L_jj
+    __shared__ int fail;
+    const int b = blockIdx.z, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    T* Ab = A + (long)b * mstride + (long)r0 * np + r0;
+    T* Wb = W + (long)b * mstride + (long)r0 * np + r0;
+    if (tid == 0) fail = 0;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = ty + 16 * a, k = tx + 16 * q;
+            as[i][k] = (k <= i) ? Ab[(long)i * np + k] : T(0);
+        }
+    leaf_core<T, DBG>(as, ws, rdv, dinv, &fail, tid);
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -291,16 +321,124 @@ __global__ void __launch_bounds__(256) k_leaf(T* __restrict__ A, T* __restrict__
             const int i = ty + 16 * a, k = tx + 16 * q;
             Wb[(long)i * np + k] = (k <= i) ? ws[i][k] : T(0);
         }
-    if (tid < 32) {
-        T s = T(0);
-        for (int i = tid; i < TILE; i += 32) s += -dev_log<T>(dinv[i]);
+    leaf_logdet<T>(dinv, tid, ldp + (long)b * ldp_stride + r0 / TILE);
+    if (tid == 0 && fail) status[b] = 1;
+}
+
+// acc[a][q] += sum_k Am[ty + 16a][k] * (BT ? Bm[tx + 16q][k] : Bm[k][tx + 16q]): a 64x64x64 product of shared-memory
+// tiles on the FP64/FP32 FMA pipe (on sm_100a the DFMA rate equals the DMMA rate; ~2 us per product)
+template <typename T, bool BT>
+__device__ __forceinline__ void mm64(const T (*Am)[TILE + 1], const T (*Bm)[TILE + 1], T acc[4][4], int tx, int ty) {
+#pragma unroll 4
+    for (int k = 0; k < TILE; k++) {
+        T av[4], bv[4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (tid == 0) {
-            ldp[(long)b * ldp_stride + r0 / TILE] = s;
-            if (fail) status[b] = 1;
-        }
+        for (int a = 0; a < 4; a++) av[a] = Am[ty + 16 * a][k];
+#pragma unroll
+        for (int q = 0; q < 4; q++) bv[q] = BT ? Bm[tx + 16 * q][k] : Bm[k][tx + 16 * q];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[a][q] = fma(av[a], bv[q], acc[a][q]);
     }
+}
+
+// A whole 128-wide node of the recursion in one CTA (two leaves and the four 64^3 products between them), so that
+// the bottom level of the tree costs one launch instead of six dependent ones:
+//   W11 = leaf(A11); L21 = A21 W11^T; T = L21 W11; A22 -= L21 L21^T; W22 = leaf(A22); W21 = -W22 T.
+template <typename T>
+__global__ void __launch_bounds__(256) k_node128(T* __restrict__ A, T* __restrict__ W, long mstride, int np, int r0,
+                                                 T* __restrict__ ldp, int ldp_stride, int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char leaf_smem_raw[];
+    typedef T Row[TILE + 1];
+    Row* as = reinterpret_cast<Row*>(leaf_smem_raw);
+    Row* w1 = reinterpret_cast<Row*>(leaf_smem_raw + 1 * leaf_tile_bytes<T>());
+    Row* w2 = reinterpret_cast<Row*>(leaf_smem_raw + 2 * leaf_tile_bytes<T>());
+    Row* pm = reinterpret_cast<Row*>(leaf_smem_raw + 3 * leaf_tile_bytes<T>());  // A21, later T
+    Row* qm = reinterpret_cast<Row*>(leaf_smem_raw + 4 * leaf_tile_bytes<T>());  // L21
+    T* rdv = reinterpret_cast<T*>(leaf_smem_raw + 5 * leaf_tile_bytes<T>());
+    T* dinv = rdv + TILE;
+    __shared__ int fail;
+    const int b = blockIdx.z, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    T* Ab = A + (long)b * mstride + (long)r0 * np + r0;
+    T* Wb = W + (long)b * mstride + (long)r0 * np + r0;
+    T* ld = ldp + (long)b * ldp_stride + r0 / TILE;
+    if (tid == 0) fail = 0;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = ty + 16 * a, k = tx + 16 * q;
+            as[i][k] = (k <= i) ? Ab[(long)i * np + k] : T(0);
+            pm[i][k] = Ab[(long)(i + TILE) * np + k];  // A21
+        }
+    leaf_core<T, 0>(as, w1, rdv, dinv, &fail, tid);
+    leaf_logdet<T>(dinv, tid, ld);
+    T acc[4][4];
+    // L21 = A21 W11^T
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[a][q] = T(0);
+    mm64<T, true>(pm, w1, acc, tx, ty);
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) qm[ty + 16 * a][tx + 16 * q] = acc[a][q];
+    // A22 (lower) into `as` while L21 settles
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = ty + 16 * a, k = tx + 16 * q;
+            acc[a][q] = (k <= i) ? Ab[(long)(i + TILE) * np + TILE + k] : T(0);
+        }
+    __syncthreads();
+    // A22 -= L21 L21^T  (negated accumulation: acc holds A22, subtract the product)
+    {
+        T prod[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) prod[a][q] = T(0);
+        mm64<T, true>(qm, qm, prod, tx, ty);
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = ty + 16 * a, k = tx + 16 * q;
+                as[i][k] = (k <= i) ? acc[a][q] - prod[a][q] : T(0);
+            }
+    }
+    // T = L21 W11 -> pm (A21 is dead: every thread finished reading it before the barrier above)
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[a][q] = T(0);
+    mm64<T, false>(qm, w1, acc, tx, ty);
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) pm[ty + 16 * a][tx + 16 * q] = acc[a][q];
+    __syncthreads();
+    leaf_core<T, 0>(as, w2, rdv, dinv, &fail, tid);
+    leaf_logdet<T>(dinv, tid, ld + 1);
+    // W21 = -W22 T
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[a][q] = T(0);
+    mm64<T, false>(w2, pm, acc, tx, ty);
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = ty + 16 * a, k = tx + 16 * q;
+            Wb[(long)i * np + k] = (k <= i) ? w1[i][k] : T(0);
+            Wb[(long)(i + TILE) * np + k] = -acc[a][q];
+            Wb[(long)(i + TILE) * np + TILE + k] = (k <= i) ? w2[i][k] : T(0);
+        }
+    if (tid == 0 && fail) status[b] = 1;
 }
 
 // u[i] = sum_{k <= i} W[i][k] v[k]   (one warp per row)
