@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--no-full-fit", action="store_true", help="skip the whole fit+predict wall-time leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--maxeval", type=int, default=150)
+    ap.add_argument("--fit-shard", default="balanced", choices=["balanced", "static"],
+                    help="multi-GPU restart loop: per-round balancing (hbegp_fit_runs_sharded) or a static split of the runs")
     ap.add_argument("--only", default="all", choices=["all", "fit-step", "predict"],
                     help="profiling aid: run just the timed fit steps or just the timed prediction, print a short line")
     return ap.parse_args()
@@ -341,7 +343,8 @@ def main():
         barrier()
         t0 = time.perf_counter()
         fk = h.FittedKernel.new(ctx, kernel, x, y, h.RNG.new_with_seed(1), args.restarts, bv(1.0, 1e-2, 1e1),
-                                maxeval=args.maxeval, shard=hd.sharded_fit_runs if world > 1 else None)
+                                maxeval=args.maxeval,
+                                shard=None if world == 1 else (hd.BalancedFit() if args.fit_shard == "balanced" else hd.sharded_fit_runs))
         barrier()
         t_fit = time.perf_counter() - t0
         t0 = time.perf_counter()

@@ -29,6 +29,9 @@ class YNorm(C.Structure):
 
 
 OBJECTIVE_FN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_long)
+BATCH_OBJECTIVE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_int))
 
 # name -> (restype, argtypes); must list every symbol include/hbegp.h declares
 PROTOTYPES = {
@@ -44,6 +47,10 @@ PROTOTYPES = {
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "hbegp_fit_runs": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                  C.POINTER(RunResult), C.c_void_p]),
+    "hbegp_fit_runs_sharded": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_int, C.c_int, ALLREDUCE_FN, C.c_void_p, C.POINTER(RunResult), C.c_void_p]),
+    "hbegp_fit_runs_with": (C.c_int, [BATCH_OBJECTIVE_FN, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_int, ALLREDUCE_FN, C.c_void_p, C.POINTER(RunResult), C.c_void_p]),
     "hbegp_pick_best_run": (C.c_int, [C.c_int, C.POINTER(RunResult)]),
     "hbegp_model_create": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_void_p, C.c_void_p]),
@@ -104,3 +111,18 @@ def check(code: int, where: str) -> int:
     if code < 0:
         raise HbegpError(code, where)
     return code
+
+
+def allreduce_callback(fn):
+    """Wraps ``fn(np.ndarray float64) -> None`` (in-place sum over all ranks) as an ``hbegp_allreduce_fn``."""
+    import numpy as np
+
+    def cb(_user, values, count):
+        try:
+            fn(np.ctypeslib.as_array(values, shape=(count,)))
+            return 0
+        except Exception as exc:  # noqa: BLE001 - must not unwind through C
+            import sys
+            print(f"hbegp all-reduce callback failed: {exc!r}", file=sys.stderr)
+            return 1
+    return ALLREDUCE_FN(cb)

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <map>
 #include <string>
@@ -1059,11 +1060,21 @@ static int configure_gemms() {
 }
 
 // ------------------------------------------------------------------------------------ restart loop
-static int fit_runs_impl(EngineBase* e, double nu, int n_runs, const double* starts, const double* blo, const double* bhi,
-                         int maxeval, hbegp_run_result* results, double* best_theta) {
-    const int p = e->d + 2;
+// The restart loop of gradmin.rs:7-33 / fit.rs:93-134 with all runs advancing in lockstep: one round = one batched
+// evaluation of every live run's next point.  `eval` evaluates a batch (the GPU, or a host objective in
+// hbegp_fit_runs_with).  With world > 1 every rank runs the same optimisers on the same values: a round's live runs
+// are dealt out round-robin, each rank evaluates its share and a sum all-reduce of the zero-padded round record
+// (lml, status, gradient per live run) gives everyone the full round -- the load stays balanced while runs finish at
+// different times, and the result is bit-identical to the single-process loop.
+using BatchEval = std::function<int(int, const double*, double*, double*, int*)>;
+
+static int fit_runs_impl(int p, const BatchEval& eval, int n_runs, const double* starts, const double* blo, const double* bhi,
+                         int maxeval, int rank, int world, hbegp_allreduce_fn allreduce, void* ar_user,
+                         hbegp_run_result* results, double* best_theta) {
     if (n_runs < 0 || (n_runs > 0 && (!starts || !blo || !bhi || !results || !best_theta)))
         return fail(HBEGP_ERR_INVALID, "fit_runs: bad arguments");
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !allreduce))
+        return fail(HBEGP_ERR_INVALID, "fit_runs: need 0 <= rank < world and an all-reduce callback when world > 1");
     std::vector<double> lb(p), ub(p);
     for (int k = 0; k < p; k++) {
         if (!(blo[k] > 0) || !(bhi[k] >= blo[k])) return fail(HBEGP_ERR_INVALID, "fit_runs: bounds must satisfy 0 < lo <= hi");
@@ -1082,9 +1093,10 @@ static int fit_runs_impl(EngineBase* e, double nu, int n_runs, const double* sta
         results[r].reserved = 0;
         for (int k = 0; k < p; k++) best_theta[(size_t)r * p + k] = starts[(size_t)r * p + k];
     }
-    std::vector<int> live;
-    std::vector<double> th, lml, grad;
-    std::vector<int> st;
+    std::vector<int> live, mine;
+    std::vector<double> th, lml, grad, thm, lmlm, gradm, xbuf;
+    std::vector<int> st, stm;
+    const int w = p + 2;  // round record per live run: lml, status, gradient
     const bool trace = getenv("HBEGP_TRACE") != nullptr;  // per-round batch sizes on stderr
     for (;;) {
         live.clear();
@@ -1098,8 +1110,39 @@ static int fit_runs_impl(EngineBase* e, double nu, int n_runs, const double* sta
         grad.resize((size_t)B * p);
         st.resize(B);
         for (int b = 0; b < B; b++) std::memcpy(&th[(size_t)b * p], opt[live[b]].ask(), sizeof(double) * p);
-        int rc = e->eval_batch(nu, B, th.data(), blo, bhi, lml.data(), grad.data(), st.data());
-        if (rc) return rc;
+        if (world == 1) {
+            int rc = eval(B, th.data(), lml.data(), grad.data(), st.data());
+            if (rc) return rc;
+        } else {
+            mine.clear();
+            for (int b = rank; b < B; b += world) mine.push_back(b);
+            const int Bm = (int)mine.size();
+            thm.resize((size_t)Bm * p);
+            lmlm.resize(Bm);
+            gradm.resize((size_t)Bm * p);
+            stm.resize(Bm);
+            for (int i = 0; i < Bm; i++) std::memcpy(&thm[(size_t)i * p], &th[(size_t)mine[i] * p], sizeof(double) * p);
+            int rc = Bm ? eval(Bm, thm.data(), lmlm.data(), gradm.data(), stm.data()) : HBEGP_OK;
+            // a failing rank must still take part in the collective; the error is reported afterwards
+            xbuf.assign((size_t)B * w + 1, 0.0);
+            xbuf[(size_t)B * w] = rc ? 1.0 : 0.0;
+            for (int i = 0; i < Bm && !rc; i++) {
+                double* rec = &xbuf[(size_t)mine[i] * w];
+                const bool ok = stm[i] == HBEGP_OK;
+                rec[0] = ok ? lmlm[i] : 0.0;
+                rec[1] = (double)stm[i];
+                for (int k = 0; k < p; k++) rec[2 + k] = ok ? gradm[(size_t)i * p + k] : 0.0;
+            }
+            if (allreduce(ar_user, xbuf.data(), (long)xbuf.size())) return fail(HBEGP_ERR_INVALID, "fit_runs: the all-reduce callback failed");
+            if (rc) return rc;
+            if (xbuf[(size_t)B * w] != 0.0) return fail(HBEGP_ERR_CUDA, "fit_runs: the evaluation failed on another rank");
+            for (int b = 0; b < B; b++) {
+                const double* rec = &xbuf[(size_t)b * w];
+                lml[b] = rec[0];
+                st[b] = (int)rec[1];
+                std::memcpy(&grad[(size_t)b * p], rec + 2, sizeof(double) * p);
+            }
+        }
         for (int b = 0; b < B; b++) {
             const int r = live[b];
             hbegp_run_result& R = results[r];
@@ -1290,9 +1333,32 @@ int hbegp_lml_grad_batch(hbegp_ctx* ctx, double nu, int B, const double* theta, 
 
 int hbegp_fit_runs(hbegp_ctx* ctx, double nu, int n_runs, const double* starts, const double* bounds_lo,
                    const double* bounds_hi, int maxeval, hbegp_run_result* results, double* best_theta) {
+    return hbegp_fit_runs_sharded(ctx, nu, n_runs, starts, bounds_lo, bounds_hi, maxeval, 0, 1, nullptr, nullptr, results, best_theta);
+}
+
+int hbegp_fit_runs_sharded(hbegp_ctx* ctx, double nu, int n_runs, const double* starts, const double* bounds_lo,
+                           const double* bounds_hi, int maxeval, int rank, int world, hbegp_allreduce_fn allreduce,
+                           void* allreduce_user, hbegp_run_result* results, double* best_theta) {
     if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");
     if (ctx->eng->n <= 0) return fail(HBEGP_ERR_INVALID, "no training data: call hbegp_set_data first");
-    return fit_runs_impl(ctx->eng, nu, n_runs, starts, bounds_lo, bounds_hi, maxeval, results, best_theta);
+    EngineBase* e = ctx->eng;
+    BatchEval eval = [&](int B, const double* th, double* lml, double* grad, int* st) {
+        return e->eval_batch(nu, B, th, bounds_lo, bounds_hi, lml, grad, st);
+    };
+    return fit_runs_impl(e->d + 2, eval, n_runs, starts, bounds_lo, bounds_hi, maxeval, rank, world, allreduce, allreduce_user,
+                         results, best_theta);
+}
+
+int hbegp_fit_runs_with(hbegp_batch_objective_fn objective, void* objective_user, int p, int n_runs, const double* starts,
+                        const double* bounds_lo, const double* bounds_hi, int maxeval, int rank, int world,
+                        hbegp_allreduce_fn allreduce, void* allreduce_user, hbegp_run_result* results, double* best_theta) {
+    if (!objective || p < 1) return fail(HBEGP_ERR_INVALID, "fit_runs_with: bad arguments");
+    BatchEval eval = [&](int B, const double* th, double* lml, double* grad, int* st) {
+        int rc = objective(objective_user, B, p, th, lml, grad, st);
+        return rc ? fail(HBEGP_ERR_INVALID, "fit_runs_with: the objective callback failed") : HBEGP_OK;
+    };
+    return fit_runs_impl(p, eval, n_runs, starts, bounds_lo, bounds_hi, maxeval, rank, world, allreduce, allreduce_user, results,
+                         best_theta);
 }
 
 int hbegp_pick_best_run(int n_runs, const hbegp_run_result* results) {

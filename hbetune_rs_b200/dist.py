@@ -1,9 +1,12 @@
 """Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink; gloo in the CPU
 tests).  Only the two parts of the path that shard naturally are sharded:
 
-* restart runs of the fit (``src/util/gradmin.rs:19-30``): run r goes to rank r mod G; after the local
-  runs an all-gather of the per-run ``(best_lml, best_eval, n_evals, final_f, status, theta[p])`` records
-  lets every rank apply the same deterministic pick (``fit.rs:116-117``: strict ``>``, earliest wins);
+* restart runs of the fit (``src/util/gradmin.rs:19-30``).  ``BalancedFit``: all ranks drive the same lockstep
+  loop, each round's live runs are dealt out round-robin and one small sum all-reduce shares the round's
+  (lml, status, gradient) records (``hbegp_fit_runs_sharded``) -- the GPUs stay evenly loaded while runs finish at
+  different times.  ``sharded_fit_runs`` is the static alternative: run r goes to rank r mod G, one all-gather of
+  the per-run ``(best_lml, best_eval, n_evals, final_f, status, theta[p])`` records at the end.  Either way every
+  rank applies the same deterministic pick (``fit.rs:116-117``: strict ``>``, earliest wins) to identical records;
 * candidate rows of a prediction: contiguous blocks, all-gather of the (mean, var) shards.
 
 The single n x n factorisation stays on one GPU (replicas only).
@@ -84,6 +87,33 @@ def sharded_fit_runs(starts: np.ndarray, run_fn: Callable):
         out[i].final_f = merged[i, 3]
         out[i].status = int(merged[i, 4])
     return out, merged[:, 5:].copy()
+
+
+def all_reduce_sum_inplace(values: np.ndarray) -> None:
+    """Sums a float64 array over all ranks in place (NCCL through a device tensor, gloo directly)."""
+    import torch
+    rank, size = world()
+    if size == 1:
+        return
+    dist = _dist()
+    dev = _device()
+    t = torch.from_numpy(values)
+    if dev.type == "cuda":
+        g = t.to(dev)
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        t.copy_(g)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+
+class BalancedFit:
+    """``shard=`` argument of ``FittedKernel.new`` / ``EstimatorGPR.shard``: the restart loop balanced per round over
+    all ranks (``hbegp_fit_runs_sharded``).  Every rank must hold the same training data and call with the same
+    arguments; every rank gets the records of all runs."""
+
+    def fit_runs(self, ctx, starts, lo, hi, nu=2.5, maxeval=150):
+        rank, size = world()
+        return ctx.fit_runs(starts, lo, hi, nu, maxeval, rank=rank, world=size, allreduce=all_reduce_sum_inplace)
 
 
 def row_block(m: int, rank: int, size: int) -> Tuple[int, int]:

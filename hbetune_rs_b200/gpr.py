@@ -200,15 +200,23 @@ class Context:
                                        _ptr(status)), "hbegp_lml_grad_batch")
         return lml, grad, status
 
-    def fit_runs(self, starts: np.ndarray, lo, hi, nu: float = 2.5, maxeval: int = 150):
+    def fit_runs(self, starts: np.ndarray, lo, hi, nu: float = 2.5, maxeval: int = 150, rank: int = 0, world: int = 1,
+                 allreduce=None):
+        """``hbegp_fit_runs``; with ``world > 1`` the balanced multi-process loop (``hbegp_fit_runs_sharded``):
+        ``allreduce(array)`` must sum the float64 array in place over all ranks."""
         starts = np.ascontiguousarray(np.atleast_2d(starts), dtype=np.float64)
         R, p = starts.shape
         lo = np.ascontiguousarray(lo, dtype=np.float64)
         hi = np.ascontiguousarray(hi, dtype=np.float64)
         res = (_lib.RunResult * R)()
         best_theta = np.empty((R, p))
-        check(lib.hbegp_fit_runs(self._h, nu, R, _ptr(starts), _ptr(lo), _ptr(hi), maxeval, res, _ptr(best_theta)),
-              "hbegp_fit_runs")
+        if world == 1:
+            check(lib.hbegp_fit_runs(self._h, nu, R, _ptr(starts), _ptr(lo), _ptr(hi), maxeval, res, _ptr(best_theta)),
+                  "hbegp_fit_runs")
+        else:
+            cb = _lib.allreduce_callback(allreduce)
+            check(lib.hbegp_fit_runs_sharded(self._h, nu, R, _ptr(starts), _ptr(lo), _ptr(hi), maxeval, rank, world, cb, None,
+                                             res, _ptr(best_theta)), "hbegp_fit_runs_sharded")
         return res, best_theta
 
     def bench_phase(self, theta, phase: int, reps: int = 3, nu: float = 2.5) -> float:
@@ -313,7 +321,9 @@ class FittedKernel:
             noise: BoundedValue, maxeval: int = 150, want_kinv: bool = False, shard=None) -> "FittedKernel":
         """``FittedKernel::new`` (``src/gpr/fit.rs:18-31, 71-176``).  ``rng`` needs ``uniform_inclusive``;
         start points are drawn in reference order (``gradmin.rs:21-24``) before any optimisation runs.
-        ``shard`` (optional) is a callable ``(starts, run_fn) -> (results, thetas)`` distributing runs."""
+        ``shard`` (optional) distributes the runs over processes: either a callable
+        ``(starts, run_fn) -> (results, thetas)`` (static split, ``dist.sharded_fit_runs``) or an object with a
+        ``fit_runs(ctx, starts, lo, hi, nu, maxeval)`` method (``dist.BalancedFit``: per-round balancing)."""
         ctx.set_data(x_train, y_train)
         lo, hi = cls._theta_bounds(kernel, noise)
         tb = [(math.log(a), math.log(b)) for a, b in zip(lo, hi)]
@@ -323,6 +333,8 @@ class FittedKernel:
         nu = kernel.k2.nu
         if shard is None:
             res, thetas = ctx.fit_runs(starts, lo, hi, nu, maxeval)
+        elif hasattr(shard, "fit_runs"):
+            res, thetas = shard.fit_runs(ctx, starts, lo, hi, nu, maxeval)
         else:
             res, thetas = shard(starts, lambda s: ctx.fit_runs(s, lo, hi, nu, maxeval))
         best = lib.hbegp_pick_best_run(len(res), res)

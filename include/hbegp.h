@@ -88,6 +88,27 @@ typedef struct hbegp_run_result {
 int hbegp_fit_runs(hbegp_ctx* ctx, double nu, int n_runs, const double* starts, const double* bounds_lo,
                    const double* bounds_hi, int maxeval, hbegp_run_result* results, double* best_theta);
 
+/* The same loop across `world` processes (one per GPU, each with its own context holding the same data): every rank
+ * passes identical arguments plus its rank.  Each round the live runs are dealt out round-robin, every rank
+ * evaluates its share and `allreduce` (called once per round on every rank) must sum `count` doubles element-wise
+ * over all ranks in place -- e.g. ncclAllReduce / torch.distributed.all_reduce(SUM).  All ranks return the records of
+ * ALL runs, bit-identical to the single-process loop (each value is summed with zeros only).  The work stays
+ * balanced while runs finish at different times (a static split of the runs leaves GPUs idle in the tail). */
+typedef int (*hbegp_allreduce_fn)(void* user, double* values, long count); /* 0 on success */
+int hbegp_fit_runs_sharded(hbegp_ctx* ctx, double nu, int n_runs, const double* starts, const double* bounds_lo,
+                           const double* bounds_hi, int maxeval, int rank, int world, hbegp_allreduce_fn allreduce,
+                           void* allreduce_user, hbegp_run_result* results, double* best_theta);
+
+/* The loop over a caller-supplied batched objective instead of the GPU (the restart loop of gradmin.rs:7-33 for any
+ * function): objective(user, B, p, theta[B*p], lml[B], grad[B*p], status[B]) returns 0 on success; status[b] != 0
+ * marks a failed evaluation (treated like a non-PD matrix, fit.rs:103-113).  rank / world / allreduce as above
+ * (0, 1, NULL for one process). */
+typedef int (*hbegp_batch_objective_fn)(void* user, int batch, int p, const double* theta, double* lml, double* grad,
+                                        int* status);
+int hbegp_fit_runs_with(hbegp_batch_objective_fn objective, void* objective_user, int p, int n_runs, const double* starts,
+                        const double* bounds_lo, const double* bounds_hi, int maxeval, int rank, int world,
+                        hbegp_allreduce_fn allreduce, void* allreduce_user, hbegp_run_result* results, double* best_theta);
+
 /* Deterministic winner pick over runs in reference order (fit.rs:116-117: strict `>`, so the earliest
  * (run, evaluation) wins ties).  Returns the winning run index or -1 if none succeeded. */
 int hbegp_pick_best_run(int n_runs, const hbegp_run_result* results);

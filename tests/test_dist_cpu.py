@@ -59,6 +59,24 @@ def _worker(rank, size, port, tmp):
         np.testing.assert_allclose(var, xs.prod(axis=1))
         mean, var = hd.sharded_predict(lambda x, wv: (x.sum(axis=1), None), xs[:1], want_variance=False)
         assert var is None and mean.shape == (1,)
+        # balanced restart loop (hbegp_fit_runs_sharded's machinery over a host objective): the per-round sum
+        # all-reduce goes through gloo; every rank must get the single-process records bit for bit
+        from tests.test_host import _quadratic_objective, _run_with
+        centers = np.array([0.3, -0.2, 1.0])
+        blo, bhi = np.exp(np.full(3, -3.0)), np.exp(np.full(3, 3.0))
+        st = np.random.default_rng(11).uniform(-2.5, 2.5, (7, 3))
+        obj1, calls1 = _quadratic_objective(centers, fail_above=2.2)
+        rc, ref2, ref2_thetas = _run_with(obj1, st, blo, bhi)
+        assert rc == 0
+        obj2, calls2 = _quadratic_objective(centers, fail_above=2.2)
+        rc, res2, thetas2 = _run_with(obj2, st, blo, bhi, rank=rank, world=size, allreduce=hd.all_reduce_sum_inplace)
+        assert rc == 0
+        for i in range(7):
+            assert (res2[i].best_eval, res2[i].n_evals, res2[i].status) == (ref2[i].best_eval, ref2[i].n_evals, ref2[i].status)
+            assert res2[i].best_lml == ref2[i].best_lml or res2[i].status != 0
+            assert res2[i].final_f == ref2[i].final_f
+        np.testing.assert_array_equal(thetas2, ref2_thetas)
+        assert len(calls2) <= len(calls1) and sum(calls2) < sum(calls1)  # only this rank's share was evaluated here
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

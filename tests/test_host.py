@@ -171,3 +171,128 @@ def test_minimizer_respects_maxeval_and_bounds():
     n = _lib.lib.hbegp_minimize_by_gradient(_lib.OBJECTIVE_FN(f), None, 2, x.ctypes.data_as(C.c_void_p),
                                             lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), 150, C.byref(fout))
     assert list(x) == [3.0, -2.0] and fout.value == 49.0 + 64.0  # the constrained optimum is the corner
+
+
+# ---- hbegp_fit_runs_with: the lockstep restart loop over a host objective (gradmin.rs:7-33)
+def _quadratic_objective(centers, fail_above=None):
+    """lml(theta) = -sum_k w_k (theta_k - c_k)^2 (one maximum per run family); status 1 where theta_0 > fail_above."""
+    from hbetune_rs_b200 import _lib
+    w = np.array([1.0, 3.0, 0.5])
+    calls = []
+
+    def cb(_user, B, p, theta, lml, grad, status):
+        calls.append(B)
+        for b in range(B):
+            th = np.array([theta[b * p + k] for k in range(p)])
+            if fail_above is not None and th[0] > fail_above:
+                status[b] = 1
+                lml[b] = float("nan")
+                continue
+            status[b] = 0
+            lml[b] = -float(np.sum(w * (th - centers) ** 2))
+            g = -2.0 * w * (th - centers)
+            for k in range(p):
+                grad[b * p + k] = g[k]
+        return 0
+    return _lib.BATCH_OBJECTIVE_FN(cb), calls
+
+
+def _run_with(objective, starts, lo, hi, rank=0, world=1, allreduce=None, maxeval=150):
+    from hbetune_rs_b200 import _lib
+    L = _lib.lib
+    starts = np.ascontiguousarray(starts, dtype=np.float64)
+    R, p = starts.shape
+    res = (_lib.RunResult * R)()
+    thetas = np.empty((R, p))
+    ar = _lib.allreduce_callback(allreduce) if allreduce is not None else _lib.ALLREDUCE_FN()
+    rc = L.hbegp_fit_runs_with(objective, None, p, R, starts.ctypes.data, lo.ctypes.data, hi.ctypes.data, maxeval, rank, world,
+                               ar, None, res, thetas.ctypes.data)
+    return rc, res, thetas
+
+
+def test_fit_runs_with_host_objective_finds_the_maximum_and_counts_evaluations():
+    centers = np.array([0.3, -0.2, 1.0])
+    obj, calls = _quadratic_objective(centers)
+    lo, hi = np.exp(np.array([-3.0, -3.0, -3.0])), np.exp(np.array([3.0, 3.0, 3.0]))
+    starts = np.random.default_rng(3).uniform(-2.5, 2.5, (6, 3))
+    rc, res, thetas = _run_with(obj, starts, lo, hi)
+    assert rc == 0
+    for r in range(6):
+        assert res[r].status == 0 and res[r].n_evals >= 2
+        np.testing.assert_allclose(thetas[r], centers, atol=1e-6)
+        assert res[r].best_lml == pytest.approx(0.0, abs=1e-10)
+        assert 0 <= res[r].best_eval < res[r].n_evals
+    # lockstep: the first round evaluates all six runs, later rounds only the live ones
+    assert calls[0] == 6 and sum(calls) == sum(res[r].n_evals for r in range(6)) and min(calls) >= 1
+
+
+def test_fit_runs_with_failed_evaluations_are_infinite_cost_not_errors():
+    centers = np.array([0.3, -0.2, 1.0])
+    obj, _ = _quadratic_objective(centers, fail_above=1.5)
+    lo, hi = np.exp(np.array([-3.0, -3.0, -3.0])), np.exp(np.array([3.0, 3.0, 3.0]))
+    starts = np.array([[2.0, 0.0, 0.0], [0.0, 0.0, 0.0]])  # run 0 starts in the failing region (fit.rs:103-113)
+    rc, res, thetas = _run_with(obj, starts, lo, hi)
+    assert rc == 0
+    assert res[1].status == 0
+    np.testing.assert_allclose(thetas[1], centers, atol=1e-6)
+    assert res[0].status == 1 and res[0].best_eval == -1  # zero gradient at +inf: the run stops where it started
+    np.testing.assert_array_equal(thetas[0], starts[0])
+
+
+def test_fit_runs_sharded_argument_validation():
+    from hbetune_rs_b200 import _lib
+    centers = np.zeros(3)
+    obj, _ = _quadratic_objective(centers)
+    lo, hi = np.full(3, 0.1), np.full(3, 10.0)
+    starts = np.zeros((2, 3))
+    assert _run_with(obj, starts, lo, hi, rank=2, world=2, allreduce=lambda a: None)[0] == _lib.ERR_INVALID
+    assert _run_with(obj, starts, lo, hi, rank=0, world=2, allreduce=None)[0] == _lib.ERR_INVALID
+    assert _run_with(obj, starts, lo, hi, rank=0, world=0)[0] == _lib.ERR_INVALID
+    assert _run_with(obj, starts, np.full(3, -1.0), hi)[0] == _lib.ERR_INVALID
+
+
+def test_fit_runs_with_two_simulated_ranks_match_one_process():
+    """Both 'ranks' in one process, stepping in turn through a shared all-reduce: every rank must end with the
+    single-process records bit for bit, and each evaluates only its round-robin share."""
+    import threading
+    centers = np.array([0.3, -0.2, 1.0])
+    lo, hi = np.exp(np.array([-3.0, -3.0, -3.0])), np.exp(np.array([3.0, 3.0, 3.0]))
+    starts = np.random.default_rng(11).uniform(-2.5, 2.5, (7, 3))
+    obj, calls1 = _quadratic_objective(centers, fail_above=2.2)
+    rc, ref, ref_thetas = _run_with(obj, starts, lo, hi)
+    assert rc == 0
+    world = 2
+    barrier = threading.Barrier(world)
+    pending = {}
+    lock = threading.Lock()
+
+    def make_allreduce(rank):
+        def ar(a):
+            with lock:
+                pending[rank] = a.copy()
+            barrier.wait()
+            total = sum(pending[r] for r in range(world))
+            barrier.wait()
+            a[:] = total
+        return ar
+
+    out = {}
+
+    def worker(rank):
+        o, calls = _quadratic_objective(centers, fail_above=2.2)
+        out[rank] = _run_with(o, starts, lo, hi, rank=rank, world=world, allreduce=make_allreduce(rank)) + (calls,)
+
+    ts = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(60) for t in ts]
+    total_calls = 0
+    for rank in range(world):
+        rc, res, thetas, calls = out[rank]
+        assert rc == 0
+        for r in range(7):
+            assert res[r].best_lml == ref[r].best_lml or (np.isnan(res[r].best_lml) and np.isnan(ref[r].best_lml))
+            assert (res[r].best_eval, res[r].n_evals, res[r].status) == (ref[r].best_eval, ref[r].n_evals, ref[r].status)
+            assert res[r].final_f == ref[r].final_f
+        np.testing.assert_array_equal(thetas, ref_thetas)
+        total_calls += sum(calls)
+    assert total_calls == sum(calls1)  # the evaluations were split, not duplicated
