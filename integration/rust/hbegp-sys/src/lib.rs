@@ -48,6 +48,14 @@ pub struct hbegp_ynorm {
 pub type hbegp_objective_fn =
     Option<unsafe extern "C" fn(x: *const c_double, grad_out: *mut c_double, user: *mut c_void) -> c_double>;
 
+/// Sums `count` doubles in place over all ranks; 0 on success.
+pub type hbegp_allreduce_fn = Option<unsafe extern "C" fn(user: *mut c_void, values: *mut c_double, count: c_long) -> c_int>;
+/// Batched objective of `hbegp_fit_runs_with`; 0 on success.
+pub type hbegp_batch_objective_fn = Option<
+    unsafe extern "C" fn(user: *mut c_void, batch: c_int, p: c_int, theta: *const c_double, lml: *mut c_double,
+                         grad: *mut c_double, status: *mut c_int) -> c_int,
+>;
+
 extern "C" {
     pub fn hbegp_version() -> *const c_char;
     pub fn hbegp_last_error() -> *const c_char;
@@ -68,6 +76,17 @@ extern "C" {
     pub fn hbegp_fit_runs(
         ctx: *mut hbegp_ctx, nu: c_double, n_runs: c_int, starts: *const c_double, bounds_lo: *const c_double,
         bounds_hi: *const c_double, maxeval: c_int, results: *mut hbegp_run_result, best_theta: *mut c_double,
+    ) -> c_int;
+    pub fn hbegp_fit_runs_sharded(
+        ctx: *mut hbegp_ctx, nu: c_double, n_runs: c_int, starts: *const c_double, bounds_lo: *const c_double,
+        bounds_hi: *const c_double, maxeval: c_int, rank: c_int, world: c_int, allreduce: hbegp_allreduce_fn,
+        allreduce_user: *mut c_void, results: *mut hbegp_run_result, best_theta: *mut c_double,
+    ) -> c_int;
+    pub fn hbegp_fit_runs_with(
+        objective: hbegp_batch_objective_fn, objective_user: *mut c_void, p: c_int, n_runs: c_int,
+        starts: *const c_double, bounds_lo: *const c_double, bounds_hi: *const c_double, maxeval: c_int, rank: c_int,
+        world: c_int, allreduce: hbegp_allreduce_fn, allreduce_user: *mut c_void, results: *mut hbegp_run_result,
+        best_theta: *mut c_double,
     ) -> c_int;
     pub fn hbegp_pick_best_run(n_runs: c_int, results: *const hbegp_run_result) -> c_int;
 
