@@ -140,6 +140,7 @@ struct EngineBase {
     cudaStream_t main_side = nullptr;
     cudaEvent_t main_a = nullptr, main_b = nullptr;
     bool use_side = true;
+    int side_max_cnt = 4;  // also use the side stream at n > 2048 for groups of at most this many matrices
     bool use_node128 = true;
     cudaEvent_t fork_ev = nullptr;
     long n = 0;
@@ -477,7 +478,8 @@ struct Engine : EngineBase {
     }
 
     int pipeline(int nu2, cudaStream_t st, int s0, int cnt, bool want_grad, bool want_kinv, Side sd = Side()) {
-        if (!(use_side && np <= 2048 && np > TILE)) sd = Side();  // large n: the GEMMs fill the GPU on their own
+        // large n with many matrices per group: the GEMMs fill the GPU on their own
+        if (!(use_side && (np <= 2048 || cnt <= side_max_cnt) && np > TILE)) sd = Side();
         if (nu2 == 5) return pipeline_nu<5>(st, s0, cnt, want_grad, want_kinv, sd);
         if (nu2 == 3) return pipeline_nu<3>(st, s0, cnt, want_grad, want_kinv, sd);
         return pipeline_nu<1>(st, s0, cnt, want_grad, want_kinv, sd);
@@ -1273,6 +1275,7 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
     }
     if (const char* s = getenv("HBEGP_SIDE")) e->use_side = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_NODE128")) e->use_node128 = atoi(s) != 0;
+    if (const char* s = getenv("HBEGP_SIDE_CNT")) e->side_max_cnt = atoi(s);
     if (const char* s = getenv("HBEGP_PAD")) {
         const bool pad = atoi(s) != 0;
         if (dtype == HBEGP_F64) static_cast<Engine<double>*>(e)->pad_batches = pad;
