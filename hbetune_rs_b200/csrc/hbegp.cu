@@ -545,6 +545,7 @@ struct Engine : EngineBase {
         auto it = graphs.find(key);
         if (it == graphs.end()) {
             const long long before = launches;
+            const double t_cap = now_ms();
             CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
             int rc = issue_chunk(nu2, cnt, want_grad, want_kinv);
             cudaGraph_t graph = nullptr;
@@ -561,6 +562,7 @@ struct Engine : EngineBase {
             cudaGraphDestroy(graph);
             if (ce != cudaSuccess) return fail(HBEGP_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
             cg.kernels = kernels;
+            if (g_trace_model) fprintf(stderr, "[hbegp] graph for %d matrices: %lld kernels, capture + instantiate %.3f ms\n", cnt, kernels, now_ms() - t_cap);
             if (graphs.size() > 256) drop_graphs();
             it = graphs.emplace(key, cg).first;
         }

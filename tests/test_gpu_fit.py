@@ -116,3 +116,46 @@ def test_fit_f32_matches_f32_oracle_fit(n, d, restarts):
     mean_ref = ogpr.predict(ref.kernel, ref.alpha, xs, x, ref.k_inv, var_ref, A)
     np.testing.assert_allclose(mean, mean_ref, rtol=0, atol=1e-3 * max(1.0, np.abs(mean_ref).max()))
     np.testing.assert_allclose(var, var_ref, rtol=0, atol=3e-4)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_restart_loop_matches_single_process(world):
+    """hbegp_fit_runs_sharded with `world` ranks simulated by threads (one context each on the same GPU, an in-process
+    sum all-reduce): every rank must return the single-process records bit for bit."""
+    import threading
+    import hbetune_rs_b200 as h
+    x, y = synth(150, 3, seed=5)
+    gk, gnoise = _kernels(h, 3)
+    lo, hi = h.FittedKernel._theta_bounds(gk, gnoise)
+    rng = np.random.default_rng(17)
+    starts = np.stack([rng.uniform(np.log(lo), np.log(hi)) for _ in range(7)])
+    with h.Context() as ctx:
+        ctx.set_data(x, y)
+        ref, ref_thetas = ctx.fit_runs(starts, lo, hi)
+    barrier = threading.Barrier(world)
+    pending, out = {}, {}
+
+    def make_allreduce(rank):
+        def ar(a):
+            pending[rank] = a.copy()
+            barrier.wait()
+            total = sum(pending[r] for r in range(world))
+            barrier.wait()
+            a[:] = total
+        return ar
+
+    def worker(rank):
+        with h.Context() as c:
+            c.set_data(x, y)
+            out[rank] = c.fit_runs(starts, lo, hi, rank=rank, world=world, allreduce=make_allreduce(rank))
+
+    ts = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(120) for t in ts]
+    assert sorted(out) == list(range(world))
+    for rank in range(world):
+        res, thetas = out[rank]
+        for r in range(7):
+            assert (res[r].best_lml, res[r].best_eval, res[r].n_evals, res[r].status, res[r].final_f) == \
+                   (ref[r].best_lml, ref[r].best_eval, ref[r].n_evals, ref[r].status, ref[r].final_f)
+        np.testing.assert_array_equal(thetas, ref_thetas)
