@@ -11,7 +11,8 @@ from .gpr import (BoundedValue, BoundsError, ConstantKernel, Context, FittedKern
                   Product, predict)
 
 from .estimator import (LINEAR, LOGARITHMIC, EstimatorGPR, SummaryStatistics, SurrogateModelGPR, YNormalize,  # noqa: F401
-                        estimate_amplitude, expected_improvement)
+                        estimate_amplitude, expected_improvement, find_best_candidate_by_ei,
+                        find_best_individual_by_confidence_bound, predicted_fitness)
 
 from .random import RNG  # noqa: F401
 

@@ -194,6 +194,37 @@ class SurrogateModelGPR:
             q1=q[0], q2=q[1], q3=q[2])
 
 
+# ---- the callers of the model that predict one point per call in the reference, on
+#      already projected feature rows (Space::project_into_features is outside the path), one device pass each
+def find_best_candidate_by_ei(candidate_features, model: SurrogateModelGPR, fmin) -> Tuple[int, float, float]:
+    """``acquisition.rs:177-202``: (index, mean, ei) of the candidate with maximal EI; ``max_by`` keeps the LAST
+    maximum; a non-comparable (NaN) EI is the reference's panic."""
+    x = np.ascontiguousarray(candidate_features, dtype=model.A)
+    if x.shape[0] == 0:
+        raise RuntimeError("there should be a candidate with maximal EI")
+    mean, ei, best = model.predict_mean_ei_device(x, fmin)
+    if np.isnan(ei).any():
+        bad = int(np.flatnonzero(np.isnan(ei))[0])
+        raise RuntimeError(f"EI should be comparable: a={ei[bad]} b={ei[bad]}")
+    return best, mean[best], ei[best]
+
+
+def find_best_individual_by_confidence_bound(individual_features, model: SurrogateModelGPR, confidence_bound) -> Tuple[int, float]:
+    """``minimize.rs:680-714``: index of the individual with the lowest confidence bound (strict ``<``: the FIRST
+    minimum stays) and the predicted mean there."""
+    x = np.ascontiguousarray(individual_features, dtype=model.A)
+    if x.shape[0] == 0:
+        raise RuntimeError("should have at least one individual")
+    _, best = model.predict_confidence_bound_device(x, confidence_bound)
+    return best, model.predict_mean(x[best])
+
+
+def predicted_fitness(individual_features, model: SurrogateModelGPR) -> np.ndarray:
+    """``FitnessOperator::get_fitness`` with ``FitnessVia::Prediction`` (``minimize.rs:654-669``) for a whole
+    population at once: the predicted means the selection compares."""
+    return model.predict_mean_a(np.ascontiguousarray(individual_features, dtype=model.A))
+
+
 class EstimatorGPR:
     """``src/core/gpr.rs:215-400`` (``Estimator::new`` takes the space; only its length is used)."""
 

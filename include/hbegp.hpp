@@ -282,6 +282,14 @@ public:
         auto r = predict_mean_ei_a(x, 1, fmin);
         return {r.first[0], r.second[0]};
     }
+    // predict_confidence_bound for m points in one pass; `best` (optional) = the index
+    // find_best_individual_by_confidence_bound keeps (minimize.rs:680-714: strict `<`, first minimum)
+    std::vector<A> predict_confidence_bound_a(const std::vector<A>& x, long m, A cb, long* best = nullptr) const {
+        std::vector<A> out(m);
+        check(hbegp_predict_confidence_bound(fitted_.model->h, &y_norm_.raw(), m, x.data(), (double)cb, out.data(), best, nullptr),
+              "hbegp_predict_confidence_bound");
+        return out;
+    }
     A predict_confidence_bound(const std::vector<A>& x, A cb) const {
         A out;
         check(hbegp_predict_confidence_bound(fitted_.model->h, &y_norm_.raw(), 1, x.data(), (double)cb, &out, nullptr, nullptr),
@@ -307,6 +315,31 @@ private:
     int d_;
 };
 
+
+// ---- the model's callers that predict one point per call in the reference, on already projected
+//      feature rows (m x d, row major), one device pass each
+struct BestCandidate {
+    long index;
+    double mean, ei;
+};
+// acquisition.rs:177-202 (max_by keeps the LAST maximum)
+template <typename A>
+BestCandidate find_best_candidate_by_ei(const std::vector<A>& candidate_features, long m, const SurrogateModelGPR<A>& model, A fmin) {
+    if (m <= 0) throw std::runtime_error("there should be a candidate with maximal EI");
+    long best = -1;
+    auto r = model.predict_mean_ei_a(candidate_features, m, fmin, &best);
+    return {best, (double)r.first[best], (double)r.second[best]};
+}
+// minimize.rs:680-714 (strict `<`: the FIRST minimum stays); returns the index and the predicted mean there
+template <typename A>
+std::pair<long, A> find_best_individual_by_confidence_bound(const std::vector<A>& individual_features, long m, int d,
+                                                           const SurrogateModelGPR<A>& model, A confidence_bound) {
+    if (m <= 0) throw std::runtime_error("should have at least one individual");
+    long best = -1;
+    model.predict_confidence_bound_a(individual_features, m, confidence_bound, &best);
+    std::vector<A> row(individual_features.begin() + best * d, individual_features.begin() + (best + 1) * d);
+    return {best, model.predict_mean(row)};
+}
 // src/core/gpr.rs:215-450
 class EstimatorGPR {
 public:

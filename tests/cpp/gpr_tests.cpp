@@ -149,6 +149,33 @@ static int run_all() {
         EXPECT_CLOSE(one.second, r.second[best], 1e-12);
     });
 
+    // the callers' selections in one device pass, with the reference's tie rules
+    run("callers_select_like_the_one_point_loops", [&] {
+        auto m = density_model();
+        std::vector<double> cand;
+        for (int i = 0; i <= 60; i++) cand.push_back(i / 60.0);
+        cand.push_back(cand[17]);  // exact duplicates: last maximum / first minimum rules decide
+        cand.push_back(cand[40]);
+        const long mm = (long)cand.size();
+        long loop_best = 0;
+        std::vector<double> eis(mm), ucbs(mm);
+        for (long i = 0; i < mm; i++) {
+            eis[i] = m.model.predict_mean_ei({cand[i]}, 1.0).second;
+            ucbs[i] = m.model.predict_confidence_bound({cand[i]}, 1.5);
+        }
+        for (long i = 1; i < mm; i++)
+            if (!(eis[i] < eis[loop_best])) loop_best = i;  // max_by: last of the maxima
+        auto bc = find_best_candidate_by_ei(cand, mm, m.model, 1.0);
+        EXPECT(bc.index == loop_best, "EI argmax %ld vs loop %ld", bc.index, loop_best);
+        EXPECT_CLOSE(bc.ei, eis[loop_best], 1e-12 + 1e-9 * std::fabs(eis[loop_best]));
+        long loop_first = 0;
+        for (long i = 1; i < mm; i++)
+            if (ucbs[i] < ucbs[loop_first]) loop_first = i;  // strict <: first of the minima
+        auto bi = find_best_individual_by_confidence_bound(cand, mm, 1, m.model, 1.5);
+        EXPECT(bi.first == loop_first, "confidence-bound argmin %ld vs loop %ld", bi.first, loop_first);
+        EXPECT_CLOSE(bi.second, m.model.predict_mean({cand[loop_first]}), 1e-12);
+    });
+
     // fit.rs:33-68 through hbegp_model_extend: history + validation samples (minimize.rs:629-644) is a block append
     run("extend_appends_to_the_prior_factorisation", [&] {
         RNG rng = RNG::new_with_seed(99);

@@ -167,3 +167,47 @@ def test_generation_sequence_matches_oracle(objective, d, gens, log_y):
         assert math.log(model.noise.value) == pytest.approx(math.log(omodel.noise.value), abs=2e-3)
         np.testing.assert_allclose(model.predict_mean_a(probe), omodel.predict_mean_a(probe), rtol=1e-4, atol=1e-6)
         x = np.concatenate([x, rng_np.random((10, d))])
+
+
+def test_callers_batched_selection_matches_the_one_point_per_call_loops():
+    """find_best_candidate_by_ei (acquisition.rs:177-202, LAST maximum) and
+    find_best_individual_by_confidence_bound (minimize.rs:680-714, FIRST minimum) as one device pass each, against
+    the reference's pattern -- a Python loop of single-point predictions with the reference's comparison rules."""
+    import hbetune_rs_b200 as h
+    n, d = 90, 3
+    x, y = _data(n, d, 11)
+    est = h.EstimatorGPR(d).with_noise_bounds(1e-2, 1e1).n_restarts_optimizer(1)
+    model = est.estimate(x, y, None, RNG.new_with_seed(3))
+    rng = np.random.default_rng(4)
+    cand = rng.random((200, d))
+    cand[150] = cand[20]  # exact ties: duplicates of the eventual winners are planted below
+    fmin = float(y.min())
+    # -- EI: loop of predict_mean_ei, max_by semantics (last maximum wins)
+    means, eis = zip(*(model.predict_mean_ei(c, fmin) for c in cand))
+    best_loop = 0
+    for i in range(1, len(eis)):
+        if not eis[i] < eis[best_loop]:  # max_by returns the last element among equals
+            best_loop = i
+    cand2 = np.concatenate([cand, cand[best_loop:best_loop + 1]])  # a later duplicate of the winner must win
+    i, mean_i, ei_i = h.find_best_candidate_by_ei(cand2, model, fmin)
+    assert i == len(cand2) - 1
+    assert mean_i == pytest.approx(means[best_loop], rel=1e-9) and ei_i == pytest.approx(eis[best_loop], rel=1e-7, abs=1e-12)
+    i, _, _ = h.find_best_candidate_by_ei(cand, model, fmin)
+    assert i == best_loop
+    # -- confidence bound: loop of predict_confidence_bound, strict < (first minimum stays)
+    cb = 1.3
+    ucb = [model.predict_confidence_bound(c, cb) for c in cand]
+    first = 0
+    for j in range(1, len(ucb)):
+        if ucb[j] < ucb[first]:
+            first = j
+    cand3 = np.concatenate([cand, cand[first:first + 1]])  # a later duplicate of the winner must NOT win
+    j, y_j = h.find_best_individual_by_confidence_bound(cand3, model, cb)
+    assert j == first
+    assert y_j == pytest.approx(model.predict_mean(cand[first]), rel=1e-12)
+    # -- FitnessVia::Prediction for a whole population
+    np.testing.assert_allclose(h.predicted_fitness(cand[:17], model), [model.predict_mean(c) for c in cand[:17]], rtol=1e-9)
+    with pytest.raises(RuntimeError):
+        h.find_best_candidate_by_ei(np.empty((0, d)), model, fmin)
+    with pytest.raises(RuntimeError):
+        h.find_best_individual_by_confidence_bound(np.empty((0, d)), model, cb)
