@@ -314,8 +314,9 @@ def main():
         t1 = ctx.bench_phase(my_thetas, 1, reps)
         t2 = ctx.bench_phase(my_thetas, 2, reps)
         t3 = ctx.bench_phase(my_thetas, 3, reps)
+        t5 = ctx.bench_phase(my_thetas, 5, max(reps, 3))  # only the K^-1 = W^T W launches (one per stream group)
         phases = {"assemble_ms": t0, "factor_inverse_ms": t1 - t0, "alpha_kinv_ms": t2 - t1, "grad_finish_ms": t3 - t2,
-                  "eval_ms": t3, "batch": len(mine)}
+                  "eval_ms": t3, "kinv_gemm_ms": t5, "batch": len(mine)}
 
     # ---- FP64 tensor peak measured live: cuBLAS DGEMM 8192^3 through torch.matmul
     peak_tf = None
@@ -381,20 +382,33 @@ def main():
         tf_fi = flops_fi / (phases["factor_inverse_ms"] * 1e-3) * 1e-12
         tf_eval = 1.0 * n ** 3 * nb / (phases["eval_ms"] * 1e-3) * 1e-12
         tf_var = float(hi_r - lo_r) * n * n / (ms_pred * 1e-3) * 1e-12
+        # Headline roofline: the largest single launch of the dominant kernel, gemm_kernel (DMMA.8x8x4) -- the
+        # K^-1 = W^T W product (n^3/3 FLOP per matrix, one launch per stream group), timed live with CUDA events on
+        # the library's stream (hbegp_bench_phase 5).  `traffic` is the ncu DRAM byte count of one such launch.
+        traffic = ncu_traffic()
+        tf_kinv = (n ** 3 / 3.0) * nb / (phases["kinv_gemm_ms"] * 1e-3) * 1e-12
+        kt = traffic.get("kinv_gemm", {})
         out["roofline"] = {
-            "bound": "tensor", "kernel": "gemm_kernel<double> (DMMA.8x8x4) inside the factor+inverse recursion",
-            "achieved": tf_fi, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf_fi / peak_tf, "traffic": None,
+            "bound": "tensor",
+            "kernel": "gemm_kernel<T,64,64,32,32,false,false> (DMMA.8x8x4): K^-1 = W^T W on the lower tiles",
+            "achieved": tf_kinv, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf_kinv / peak_tf,
+            "traffic": kt.get("traffic"), "algorithmic_bytes": kt.get("algorithmic_bytes"),
+            "traffic_note": "DRAM bytes of one ncu --set full launch over 17 matrices (profiles/r01_fit_kernels_ncu_raw.csv); "
+                            "algorithmic = 8 n^2 bytes per matrix (W lower read once, K^-1 lower written once)",
+            "launch_ms": phases["kinv_gemm_ms"], "matrices": nb,
             "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul f64) measured in this run; MEASURED_PEAKS.json has no FP64 entry",
-            "algorithmic": "2 n^3 / 3 FLOP per evaluation (Cholesky factor n^3/3 + its triangular inverse n^3/3)",
+            "algorithmic": "n^3 / 3 FLOP per matrix (lower tiles of W^T W, K restricted to k >= row tile)",
         }
         out["phases"] = phases
-        traffic = ncu_traffic()
         t_dense = (phases["factor_inverse_ms"] + phases["alpha_kinv_ms"]) * 1e-3
         tf_dense = 1.0 * n ** 3 * nb / t_dense * 1e-12
         out["cholesky_fp64_tflops"] = tf_fi
         out["lml_eval_fp64_tflops"] = tf_eval
         out["predict_var_fp64_tflops"] = tf_var
         out["rooflines"] = {
+            "factor_inverse_phase": {"bound": "tensor", "achieved": tf_fi, "peak": peak_tf, "frac": tf_fi / peak_tf, "unit": "TFLOP/s",
+                                     "what": "2 n^3 / 3 FLOP per evaluation (Cholesky factor n^3/3 + its triangular inverse n^3/3) over the "
+                                             "whole recursion phase: k_node128 / k_leaf chains + 4 gemm_kernel launches per node"},
             "lml_eval_n3": {"achieved": tf_eval, "peak": peak_tf, "frac": tf_eval / peak_tf, "unit": "TFLOP/s"},
             "dense_phases_n3": {"achieved": tf_dense, "peak": peak_tf, "frac": tf_dense / peak_tf, "unit": "TFLOP/s",
                                 "what": "all gemm_kernel + k_leaf launches (factor, inverse, K^-1 = W^T W): n^3 FLOP per evaluation"},

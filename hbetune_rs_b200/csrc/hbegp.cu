@@ -429,7 +429,8 @@ struct Engine : EngineBase {
     }
 
     // `phase` truncates the pipeline for the benchmark's per-phase timings (hbegp_bench_phase):
-    // 0 = assembly only, 1 = + factor/inverse recursion, 2 = + alpha and K^-1, 3 (default) = everything.
+    // 0 = assembly only, 1 = + factor/inverse recursion, 2 = + alpha and K^-1, 3 (default) = everything,
+    // 5 = only the K^-1 = W^T W launches (one per stream group) on the W left by the previous evaluation.
     int phase = 3;
 
     template <int NU2>
@@ -443,6 +444,7 @@ struct Engine : EngineBase {
         T* tp = (T*)tpart.p + (size_t)s0 * nchunks() * np;
         double* gp = (double*)gpart.p + (size_t)s0 * ntiles_lower() * p();
         const size_t xsm = 2 * (size_t)d * TILE * sizeof(T);
+        if (phase == 5) return lauum(st, Ab, Wb, cnt);  // benchmark only: the K^-1 product on the W of the last evaluation
         k_scale_x<T><<<dim3((np + 255) / 256, d, cnt), 256, 0, st>>>((const T*)dX.p, (int)n, d, np, pr, p(), xs);
         launches++;
         k_assemble<T, NU2><<<dim3(ntiles_lower(), 1, cnt), 256, xsm, st>>>(xs, (int)n, d, np, pr, p(), Ab, mstride(), 0);

@@ -209,7 +209,8 @@ int hbegp_debug_factor(hbegp_ctx* ctx, double nu, const double* theta, void* k, 
 
 /* Times (CUDA events on the context's stream, average of `reps` after one warm-up) a truncated batched
  * evaluation of B thetas: phase 0 = kernel-matrix assembly, 1 = + factor/inverse recursion, 2 = + alpha and
- * K^-1 = W^T W, 3 = the whole LML + gradient evaluation.  Used by bench.py for the per-kernel rooflines. */
+ * K^-1 = W^T W, 3 = the whole LML + gradient evaluation, 5 = only the K^-1 = W^T W product launches (on the W
+ * the previous evaluation left).  Used by bench.py for the per-kernel rooflines. */
 int hbegp_bench_phase(hbegp_ctx* ctx, double nu, int B, const double* theta, int phase, int reps, float* ms_out);
 
 #ifdef __cplusplus
