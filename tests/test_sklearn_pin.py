@@ -70,3 +70,26 @@ def test_cuda_lml_gradient_and_prediction_match_sklearn(n, d, nu):
         np.testing.assert_allclose(gmean, mean, rtol=0, atol=1e-9 * max(1.0, np.abs(mean).max()))
         want = np.maximum(std ** 2 - math.exp(theta[0]) + 1e-5, 0.0)
         np.testing.assert_allclose(gvar, want, rtol=0, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_fit_reaches_the_optimum_sklearn_finds():
+    """The fitted hyper-parameters cannot be compared run for run (NLopt / L-BFGS-B / this library's L-BFGS are three
+    different optimisers), but with the same bounds and enough restarts all must reach the same maximum of the LML."""
+    import hbetune_rs_b200 as h
+    n, d = 80, 2
+    x, y = synth(n, d, seed=21)
+    bv = h.BoundedValue
+    kernel = h.Product(h.ConstantKernel(bv(1.0, 1e-2, 1e2)), h.Matern(2.5, [bv(1.0, 1e-2, 1e2)] * d))
+    with h.Context() as ctx:
+        fk = h.FittedKernel.new(ctx, kernel, x, y, h.RNG.new_with_seed(5), 10, bv(1.0, 1e-3, 1e1))
+    k = (ConstantKernel(1.0, (1e-2, 1e2)) * Matern(length_scale=[1.0] * d, length_scale_bounds=(1e-2, 1e2), nu=2.5)
+         + WhiteKernel(1.0, (1e-3, 1e1)))
+    gp = skl.GaussianProcessRegressor(kernel=k, alpha=0.0, n_restarts_optimizer=10, random_state=0).fit(x, y)
+    sk_lml = gp.log_marginal_likelihood_value_
+    assert fk.lml >= sk_lml - 1e-5 * abs(sk_lml)
+    assert fk.lml <= sk_lml + 1e-3 * abs(sk_lml) + 1e-3  # same maximum, not a different basin
+    th_sk = gp.kernel_.theta  # [ln c, ln l_1.., ln noise]
+    ours = np.array([math.log(fk.kernel.k1.constant.value)] + [math.log(l.value) for l in fk.kernel.k2.length_scale]
+                    + [math.log(fk.noise.value)])
+    np.testing.assert_allclose(ours, th_sk, atol=5e-3)
