@@ -321,8 +321,9 @@ def main():
     # ---- FP64 tensor peak measured live: cuBLAS DGEMM 8192^3 through torch.matmul
     peak_tf = None
     if rank == 0:
-        a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
-        b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+        torch.backends.cuda.matmul.allow_tf32 = False  # the f32 path computes in true FP32 (FFMA), so does its denominator
+        a = torch.randn(8192, 8192, dtype=tdt, device="cuda")
+        b = torch.randn(8192, 8192, dtype=tdt, device="cuda")
         torch.matmul(a, b)
         best = 1e30
         for _ in range(3):
@@ -389,14 +390,19 @@ def main():
         tf_kinv = (n ** 3 / 3.0) * nb / (phases["kinv_gemm_ms"] * 1e-3) * 1e-12
         kt = traffic.get("kinv_gemm", {})
         out["roofline"] = {
-            "bound": "tensor",
-            "kernel": "gemm_kernel<T,64,64,32,32,false,false> (DMMA.8x8x4): K^-1 = W^T W on the lower tiles",
+            "bound": "tensor" if args.dtype == "f64" else "fp32-fma",
+            "kernel": ("gemm_kernel<double,64,64,32,32,false,false> (DMMA.8x8x4)" if args.dtype == "f64" else
+                       "gemm_kernel<float,64,64,32,32,false,false> (FFMA micro-kernel; TF32 is not parity-safe here)")
+                      + ": K^-1 = W^T W on the lower tiles",
             "achieved": tf_kinv, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf_kinv / peak_tf,
-            "traffic": kt.get("traffic"), "algorithmic_bytes": kt.get("algorithmic_bytes"),
+            "traffic": kt.get("traffic") if args.dtype == "f64" and n == 4096 else None,
+            "algorithmic_bytes": kt.get("algorithmic_bytes") if args.dtype == "f64" and n == 4096 else None,
             "traffic_note": "DRAM bytes of one ncu --set full launch over 17 matrices (profiles/r01_fit_kernels_ncu_raw.csv); "
                             "algorithmic = 8 n^2 bytes per matrix (W lower read once, K^-1 lower written once)",
             "launch_ms": phases["kinv_gemm_ms"], "matrices": nb,
-            "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul f64) measured in this run; MEASURED_PEAKS.json has no FP64 entry",
+            "peak_source": ("cuBLAS DGEMM 8192^3 (torch.matmul f64) measured in this run; MEASURED_PEAKS.json has no FP64 entry"
+                            if args.dtype == "f64" else
+                            "cuBLAS SGEMM 8192^3 in true FP32 (torch.matmul f32, TF32 off) measured in this run"),
             "algorithmic": "n^3 / 3 FLOP per matrix (lower tiles of W^T W, K restricted to k >= row tile)",
         }
         out["phases"] = phases
