@@ -19,6 +19,7 @@ for n, d, B in ((1024, 8, 33), (1024, 8, 5), (2048, 16, 17), (4096, 16, 9), (409
     ctx = h.Context(0, h.F64)
     ctx.set_data(x, y)
     ctx.bench_phase(th, 3, 2)
-    t = [ctx.bench_phase(th, ph, 10 if n <= 2048 else 3) for ph in (0, 1, 3)]
-    print(f"[{tag}] n={n} d={d} B={B}: factor+inverse {t[1] - t[0]:.3f} ms, whole evaluation {t[2]:.3f} ms", flush=True)
+    t = [ctx.bench_phase(th, ph, 10 if n <= 2048 else 3) for ph in (0, 1, 2, 3)]
+    print(f"[{tag}] n={n} d={d} B={B}: assemble {t[0]:.3f} factor+inverse {t[1] - t[0]:.3f} alpha+kinv {t[2] - t[1]:.3f} "
+          f"grad+finish {t[3] - t[2]:.3f} whole evaluation {t[3]:.3f} ms", flush=True)
     del ctx
