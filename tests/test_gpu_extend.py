@@ -184,3 +184,43 @@ def test_estimator_extend_appends_validation_samples():
     m2, v2 = ref.model.predict(xs)
     np.testing.assert_allclose(m1, m2, rtol=0, atol=1e-9)
     np.testing.assert_allclose(v1, v2, rtol=0, atol=1e-9)
+
+
+def test_model_buffers_are_recycled_not_leaked():
+    """The tuner replaces its model every generation: destroyed models hand their buffers to the context's pool, so
+    device memory stays flat over many generations and the pool goes away with the context."""
+    import torch
+    import hbetune_rs_b200 as h
+    d, A = 4, np.float64
+    x, y = synth(900, d, seed=13)
+    th = _theta(d)
+    xs = np.random.default_rng(1).random((300, d))
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    ctx = _ctx(A)
+    model, low = None, None
+    for gen in range(30):
+        n = 600 + 10 * gen
+        ctx.set_data(x[:n], y[:n])
+        model = ctx.model(th) if model is None or gen % 3 else h.Model(ctx, prior=model)
+        model.predict(xs)
+        free, _ = torch.cuda.mem_get_info()
+        if gen == 5:
+            low = free
+    assert low - free < 64 << 20  # no growth between generation 5 and 29 beyond the slowly growing n x n factor
+    model.close()
+    ctx.close()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 << 20  # everything (workspaces, pool) returned with the context
+
+
+def test_size_limits_are_reported():
+    import hbetune_rs_b200 as h
+    from hbetune_rs_b200._lib import HbegpError
+    ctx = _ctx()
+    with pytest.raises(HbegpError):
+        ctx.set_data(np.zeros((10, 300)), np.zeros(10))  # more features than the shared-memory tiles hold
+    x, y = synth(50, 2)
+    ctx.set_data(x, y)  # the context stays usable
+    assert np.isfinite(ctx.lml_grad_batch(_theta(2)[None, :])[0][0])
