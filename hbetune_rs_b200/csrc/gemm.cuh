@@ -67,6 +67,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// 1: early-fragment main loop for f64 (default; +2..6 % on B200, probes/gemm_early.cu), 0: the plain loop
+#ifndef HBEGP_EARLY
+#define HBEGP_EARLY 1
+#endif
+
 template <typename T, int BM, int BN, int WM, int WN, bool A_KMAJOR, bool B_KMAJOR, int BK_ = HBEGP_BK, int STAGES_ = HBEGP_STAGES>
 struct GemmCfg {
     static constexpr int BK = BK_;
@@ -191,14 +196,65 @@ __global__ void __launch_bounds__(GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR,
     // warp-tile-relative row of accumulator slot i / column of slot j (see the two micro-kernels below)
     auto row_of = [&](int i) { return (F64 || A_KMAJOR) ? i * 8 + lr : FM * lr + i; };
     auto col_of = [&](int j) { return F64 ? j * 8 + 2 * lc : (B_KMAJOR ? j * 4 + lc : FN * lc + j); };
-    for (int kt = 0; kt < nk; kt++) {
+#if HBEGP_EARLY
+    // Early-fragment variant (f64): the barrier of iteration kt also publishes stage kt + 1, so the operand fragments
+    // of the first k4 step of the next stage are fetched during this iteration and no shared-memory latency sits
+    // between the barrier and the first DMMA.
+    T a_n[FM], b_n[FN];
+    auto load_frag = [&](const T* sA, const T* sB, int ks, T* a, T* b) {
+        const int k = ks * 4 + lc;
+#pragma unroll
+        for (int i = 0; i < FM; i++) {
+            int row = wm * WM + i * 8 + lr;
+            a[i] = A_KMAJOR ? sA[row * Cfg::A_STRIDE + k] : sA[k * Cfg::A_STRIDE + row];
+        }
+#pragma unroll
+        for (int j = 0; j < FN; j++) {
+            int col = wn * WN + j * 8 + lr;
+            b[j] = B_KMAJOR ? sB[col * Cfg::B_STRIDE + k] : sB[k * Cfg::B_STRIDE + col];
+        }
+    };
+    if constexpr (F64) {
         cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (nk > 0) load_frag(smem, smem + Cfg::A_ELEMS, 0, a_n, b_n);
+    }
+#endif
+    for (int kt = 0; kt < nk; kt++) {
+#if HBEGP_EARLY
+        if constexpr (F64) cp_async_wait<(STAGES >= 3 ? STAGES - 3 : 0)>();
+        else cp_async_wait<STAGES - 2>();
+#else
+        cp_async_wait<STAGES - 2>();
+#endif
         __syncthreads();
         if (kt + STAGES - 1 < nk) issue(kt + STAGES - 1);
         cp_async_commit();
         const T* sA = smem + (kt % STAGES) * Cfg::STAGE_ELEMS;
         const T* sB = sA + Cfg::A_ELEMS;
         if constexpr (F64) {
+#if HBEGP_EARLY
+#pragma unroll
+            for (int ks = 0; ks < BK / 4; ks++) {
+                T a[FM], b[FN];
+                if (ks == 0) {
+#pragma unroll
+                    for (int i = 0; i < FM; i++) a[i] = a_n[i];
+#pragma unroll
+                    for (int j = 0; j < FN; j++) b[j] = b_n[j];
+                } else {
+                    load_frag(sA, sB, ks, a, b);
+                }
+#pragma unroll
+                for (int i = 0; i < FM; i++)
+#pragma unroll
+                    for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+            if (kt + 1 < nk) {
+                const T* nA = smem + ((kt + 1) % STAGES) * Cfg::STAGE_ELEMS;
+                load_frag(nA, nA + Cfg::A_ELEMS, 0, a_n, b_n);
+            }
+#else
 #pragma unroll
             for (int ks = 0; ks < BK / 4; ks++) {
                 T a[FM], b[FN];
@@ -218,6 +274,7 @@ __global__ void __launch_bounds__(GemmCfg<T, BM, BN, WM, WN, A_KMAJOR, B_KMAJOR,
 #pragma unroll
                     for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
+#endif
         } else {
             // FP32 (FFMA): (WM/8) x (WN/4) outputs per thread — 4 x 8 for the 64x64 tile, 8 x 8 for 128x128 —
             // operands fetched four k at a time with 16-byte shared loads.  Thread-to-row/column mapping follows
