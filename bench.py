@@ -401,8 +401,9 @@ def main():
             "achieved": tf_kinv, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf_kinv / peak_tf,
             "traffic": kt.get("traffic") if args.dtype == "f64" and n == 4096 else None,
             "algorithmic_bytes": kt.get("algorithmic_bytes") if args.dtype == "f64" and n == 4096 else None,
-            "traffic_note": "DRAM bytes of one ncu --set full launch over 17 matrices (profiles/r01_fit_kernels_ncu_raw.csv); "
-                            "algorithmic = 8 n^2 bytes per matrix (W lower read once, K^-1 lower written once)",
+            "traffic_note": f"DRAM bytes of one ncu --set full launch over {kt.get('matrices', '?')} matrices "
+                            "(profiles/r01_kinv_gemm_early_ncu_raw.csv); algorithmic = 8 n (n + 1) bytes per matrix "
+                            "(W lower read once, K^-1 lower written once)",
             "launch_ms": phases["kinv_gemm_ms"], "matrices": nb,
             "peak_source": ("cuBLAS DGEMM 8192^3 (torch.matmul f64) measured in this run; MEASURED_PEAKS.json has no FP64 entry"
                             if args.dtype == "f64" else
