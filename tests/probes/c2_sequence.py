@@ -3,7 +3,7 @@ the GP refitted every generation from the previous model (src/core/minimize.rs:4
 a seeded sampler supplies the 10 new points per generation.  Reports the GP time of the whole run on the GPU and
 the oracle's CPU time for a bounded sample of generations."""
 import json, math, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import hbetune_rs_b200 as h
 from oracle import adapter as oad

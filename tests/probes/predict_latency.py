@@ -1,6 +1,6 @@
 """Probe: latency of batch-of-1 predictions (the reference's callers predict one point at a time)."""
 import math, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import hbetune_rs_b200 as h
 from tests.util import synth
