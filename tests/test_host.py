@@ -117,11 +117,18 @@ def test_gpu_arm_of_bench_does_not_import_the_oracle():
     top_level = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
     names = [getattr(n, "module", None) or n.names[0].name for n in top_level]
     assert not any(str(m).startswith(("oracle", "tests")) for m in names), names
-    for sub in ("hbetune_rs_b200",):
+    # the product package and the GPU-only probes never touch the oracle (oracle-based probes live in tests/probes)
+    for sub in ("hbetune_rs_b200", "probes"):
         for fn in os.listdir(os.path.join(ROOT, sub)):
             if fn.endswith(".py"):
                 text = open(os.path.join(ROOT, sub, fn)).read()
-                assert "import oracle" not in text and "from oracle" not in text, fn
+                assert "import oracle" not in text and "from oracle" not in text and "tests.util" not in text, fn
+    for fn in os.listdir(os.path.join(ROOT, "hbetune_rs_b200", "csrc")) + os.listdir(os.path.join(ROOT, "include")):
+        path = os.path.join(ROOT, "hbetune_rs_b200", "csrc", fn)
+        if not os.path.exists(path):
+            path = os.path.join(ROOT, "include", fn)
+        if fn.endswith((".cu", ".cuh", ".h", ".hpp")):
+            assert "oracle/" not in open(path).read(), fn
 
 
 def test_c_abi_rejects_bad_arguments_without_crashing():
