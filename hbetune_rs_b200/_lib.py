@@ -60,6 +60,13 @@ PROTOTYPES = {
     "hbegp_model_n": (C.c_long, [C.c_void_p]),
     "hbegp_model_dim": (C.c_int, [C.c_void_p]),
     "hbegp_predict": (C.c_int, [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_long)]),
+    "hbegp_predict_warn_values": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "hbegp_kernel_matrix": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p,
+                                      C.c_void_p]),
+    "hbegp_kernel_theta_grad": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
+    "hbegp_kernel_diag": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_long, C.c_void_p]),
+    "hbegp_lbfgs_set_tolerances": (C.c_int, [C.c_double, C.c_double]),
     "hbegp_predict_device": (C.c_int, [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hbegp_predict_mean_ei": (C.c_int, [C.c_void_p, C.POINTER(YNorm), C.c_long, C.c_void_p, C.c_double, C.c_void_p,
                                         C.c_void_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]),
@@ -79,6 +86,7 @@ PROTOTYPES = {
     "hbegp_normal_inverse_cdf": (C.c_double, [C.c_double, C.c_double, C.c_double]),
     "hbegp_bench_phase": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                     C.POINTER(C.c_float)]),
+    "hbegp_debug_poison": (C.c_int, [C.c_void_p]),
     "hbegp_debug_factor": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(C.c_int)]),
 }

@@ -158,6 +158,10 @@ struct EngineBase {
     virtual int model_extend(Model* prior, Model** out, double* lml, void* alpha_out, void* kinv_out, int* appended) = 0;
     virtual int debug_factor(double nu, const double* theta, void* k, void* w, void* kinv, int* status) = 0;
     virtual int bench_phase(double nu, int B, const double* theta, int phase, int reps, float* ms_out) = 0;
+    virtual int debug_poison() = 0;
+    virtual int kernel_matrix(double nu, int d, const double* theta, long n1, const void* x1, long n2, const void* x2, void* out) = 0;
+    virtual int kernel_theta_grad(double nu, int d, const double* theta, long n, const void* x, void* k_out, void* grad_out) = 0;
+    double next_model_noise = 0.0;  // clamped noise of the model being built (fit.rs:164; see Model::noise_clamped)
 };
 
 struct Model {
@@ -169,11 +173,20 @@ struct Model {
     DevBuf W, alpha, xsT, ls;  // inverse Cholesky factor (np x np), alpha (np), scaled X^T (d x np), length scales
     DevBuf ldp;                // sum of ln L_ii per 64-row leaf (kept for model_extend)
     std::vector<double> prm_h; // [noise, c, l_1..l_d] as evaluated (after clamping), in the data type's precision
+    // noise.with_clamped_value(exp(theta_0) rounded through A) (fit.rs:164, gpr.rs:322): what `extend` evaluates with.
+    // prm_h[0] is the unclamped value the fit evaluated (fit.rs:96 does not clamp); they differ only when the optimum
+    // sits outside the noise bounds by rounding.
+    double noise_clamped = 0.0;
+    // values < -sqrt(1e-5) of the last host prediction (predict.rs:39-46 lists them), in row order
+    DevBuf warn_rows, warn_vals;
+    std::vector<double> last_warn_vals;
+    std::vector<long> last_warn_rows;
+    static constexpr int kWarnCap = 4096;
     DevBuf kstar, part, pmean, nbelow, xs_tmp, mean_tmp, var_tmp;
     void release_all() {
         W.release(); alpha.release(); xsT.release(); ls.release(); ldp.release();
         kstar.release(); part.release(); pmean.release(); nbelow.release(); xs_tmp.release(); mean_tmp.release(); var_tmp.release();
-        acq1.release(); acq2.release(); argv.release(); argi.release();
+        acq1.release(); acq2.release(); argv.release(); argi.release(); warn_rows.release(); warn_vals.release();
     }
     virtual ~Model() {
         release_all();
@@ -186,7 +199,7 @@ struct Model {
     DevBuf acq1, acq2, argv, argi;
     void use_pool(BufPool* pl) {
         for (DevBuf* b : {&W, &alpha, &xsT, &ls, &ldp, &kstar, &part, &pmean, &nbelow, &xs_tmp, &mean_tmp, &var_tmp, &acq1, &acq2,
-                          &argv, &argi})
+                          &argv, &argi, &warn_rows, &warn_vals})
             b->pool = pl;
     }
 };
@@ -643,6 +656,111 @@ struct Engine : EngineBase {
         return HBEGP_OK;
     }
 
+    // trait Kernel::kernel(x1, x2) for Product<ConstantKernel, Matern> (src/gpr/kernel.rs:10-14, product_kernel.rs:36-38,
+    // matern_kernel.rs:37-80) through the PRODUCTION cross-kernel code: x2 is scaled with k_scale_x and K(x1, x2) is
+    // the k* tile output of k_kstar_mean (the kernel that feeds the predictive mean and variance).
+    template <int NU2>
+    int kernel_matrix_nu(int dd, const double* theta, long n1, const void* x1, long n2, const void* x2, void* out) {
+        const int np2 = round_up(n2, TILE);
+        if ((2 * (size_t)dd * TILE + 2 * TILE) * sizeof(T) > kMaxFeatureSmem) return fail(HBEGP_ERR_UNSUPPORTED, "kernel_matrix: too many features");
+        std::vector<T> prm_h(dd + 2);
+        prm_h[0] = T(0);
+        for (int k = 1; k < dd + 2; k++) prm_h[k] = (T)std::exp(theta[k - 1]);
+        const long chunk = 4096;
+        DevBuf dx1, dx2, dprm, dxsT, dal, dmean, dks, dout;
+        int rc = HBEGP_OK;
+        auto done = [&](int code) {
+            for (DevBuf* b : {&dx1, &dx2, &dprm, &dxsT, &dal, &dmean, &dks, &dout}) b->release();
+            return code;
+        };
+        if ((rc = dx1.ensure((size_t)n1 * dd * sizeof(T))) || (rc = dx2.ensure((size_t)n2 * dd * sizeof(T))) ||
+            (rc = dprm.ensure((size_t)(dd + 2) * sizeof(T))) || (rc = dxsT.ensure((size_t)dd * np2 * sizeof(T))) ||
+            (rc = dal.ensure((size_t)np2 * sizeof(T))) || (rc = dmean.ensure((size_t)chunk * sizeof(T))) ||
+            (rc = dks.ensure((size_t)chunk * np2 * sizeof(T))) || (rc = dout.ensure((size_t)chunk * n2 * sizeof(T))))
+            return done(rc);
+        cudaStream_t st = stream;
+        cudaError_t ce = cudaMemcpyAsync(dx1.p, x1, (size_t)n1 * dd * sizeof(T), cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(dx2.p, x2, (size_t)n2 * dd * sizeof(T), cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(dprm.p, prm_h.data(), (size_t)(dd + 2) * sizeof(T), cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(dal.p, 0, (size_t)np2 * sizeof(T), st);
+        if (ce != cudaSuccess) return done(fail(HBEGP_ERR_CUDA, std::string("kernel_matrix: ") + cudaGetErrorString(ce)));
+        k_scale_x<T><<<dim3((np2 + 255) / 256, dd, 1), 256, 0, st>>>((const T*)dx2.p, (int)n2, dd, np2, (const T*)dprm.p, dd + 2, (T*)dxsT.p);
+        launches++;
+        const size_t ksm = (2 * (size_t)dd * TILE + TILE) * sizeof(T);
+        for (long row0 = 0; row0 < n1; row0 += chunk) {
+            const long rows = std::min(chunk, n1 - row0);
+            const int rows_p = round_up(rows, TILE);
+            k_kstar_mean<T, NU2><<<dim3((unsigned)(rows_p / TILE), 1), 256, ksm, st>>>(
+                (const T*)dx1.p, n1, row0, dd, (const T*)dxsT.p, (int)n2, np2, (const T*)dprm.p + 2, prm_h[1], (const T*)dal.p,
+                (T*)dks.p, (T*)dmean.p - row0, np2 / TILE, nullptr, rows_p);
+            k_copy_cols<T><<<dim3((unsigned)((n2 + 255) / 256), (unsigned)rows), 256, 0, st>>>((const T*)dks.p, np2, rows, (int)n2, (T*)dout.p);
+            launches += 2;
+            ce = cudaGetLastError();
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync((T*)out + row0 * n2, dout.p, (size_t)rows * n2 * sizeof(T), cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+            if (ce != cudaSuccess) return done(fail(HBEGP_ERR_CUDA, std::string("kernel_matrix: ") + cudaGetErrorString(ce)));
+        }
+        return done(HBEGP_OK);
+    }
+
+    int kernel_matrix(double nu, int dd, const double* theta, long n1, const void* x1, long n2, const void* x2, void* out) override {
+        int nu2, rc;
+        if ((rc = nu_to_nu2(nu, &nu2))) return rc;
+        if (dd <= 0 || !theta || n1 < 0 || n2 < 0 || ((n1 > 0 && n2 > 0) && (!x1 || !x2 || !out))) return fail(HBEGP_ERR_INVALID, "kernel_matrix: bad arguments");
+        if (n1 == 0 || n2 == 0) return HBEGP_OK;
+        CUDA_TRY(cudaSetDevice(device));
+        if (nu2 == 5) return kernel_matrix_nu<5>(dd, theta, n1, x1, n2, x2, out);
+        if (nu2 == 3) return kernel_matrix_nu<3>(dd, theta, n1, x1, n2, x2, out);
+        return kernel_matrix_nu<1>(dd, theta, n1, x1, n2, x2, out);
+    }
+
+    // trait Kernel::theta_grad(x) -> (K (n, n), dK/dtheta (n, n, d + 1)) (kernel.rs:16-21, product_kernel.rs:40-70).
+    int kernel_theta_grad(double nu, int dd, const double* theta, long nn, const void* x, void* k_out, void* grad_out) override {
+        int nu2, rc;
+        if ((rc = nu_to_nu2(nu, &nu2))) return rc;
+        if (dd <= 0 || !theta || nn < 0 || (nn > 0 && !x)) return fail(HBEGP_ERR_INVALID, "kernel_theta_grad: bad arguments");
+        if (nn == 0 || (!k_out && !grad_out)) return HBEGP_OK;
+        if ((double)nn * nn * (dd + 1) * sizeof(T) > 8e9) return fail(HBEGP_ERR_NOMEM, "kernel_theta_grad: the (n, n, d + 1) tensor exceeds 8 GB");
+        CUDA_TRY(cudaSetDevice(device));
+        std::vector<T> ls_h(dd);
+        for (int k = 0; k < dd; k++) ls_h[k] = (T)std::exp(theta[1 + k]);
+        const T c = (T)std::exp(theta[0]);
+        DevBuf dx, dls, dk, dg;
+        auto done = [&](int code) {
+            for (DevBuf* b : {&dx, &dls, &dk, &dg}) b->release();
+            return code;
+        };
+        if ((rc = dx.ensure((size_t)nn * dd * sizeof(T))) || (rc = dls.ensure((size_t)dd * sizeof(T))) ||
+            (k_out && (rc = dk.ensure((size_t)nn * nn * sizeof(T)))) ||
+            (grad_out && (rc = dg.ensure((size_t)nn * nn * (dd + 1) * sizeof(T)))))
+            return done(rc);
+        cudaStream_t st = stream;
+        cudaError_t ce = cudaMemcpyAsync(dx.p, x, (size_t)nn * dd * sizeof(T), cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(dls.p, ls_h.data(), (size_t)dd * sizeof(T), cudaMemcpyHostToDevice, st);
+        if (ce != cudaSuccess) return done(fail(HBEGP_ERR_CUDA, std::string("kernel_theta_grad: ") + cudaGetErrorString(ce)));
+        dim3 grid((unsigned)((nn + 127) / 128), (unsigned)nn);
+        if (nu2 == 5) k_kernel_theta_grad<T, 5><<<grid, 128, 0, st>>>((const T*)dx.p, (int)nn, dd, (const T*)dls.p, c, (T*)dk.p, (T*)dg.p);
+        else if (nu2 == 3) k_kernel_theta_grad<T, 3><<<grid, 128, 0, st>>>((const T*)dx.p, (int)nn, dd, (const T*)dls.p, c, (T*)dk.p, (T*)dg.p);
+        else k_kernel_theta_grad<T, 1><<<grid, 128, 0, st>>>((const T*)dx.p, (int)nn, dd, (const T*)dls.p, c, (T*)dk.p, (T*)dg.p);
+        launches++;
+        ce = cudaGetLastError();
+        if (ce == cudaSuccess && k_out) ce = cudaMemcpyAsync(k_out, dk.p, (size_t)nn * nn * sizeof(T), cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess && grad_out) ce = cudaMemcpyAsync(grad_out, dg.p, (size_t)nn * nn * (dd + 1) * sizeof(T), cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) return done(fail(HBEGP_ERR_CUDA, std::string("kernel_theta_grad: ") + cudaGetErrorString(ce)));
+        return done(HBEGP_OK);
+    }
+
+    // Fills the batched workspaces (K / L / K^-1 and W = L^-1 of every slot) with NaN bit patterns: a test aid that
+    // proves no kernel reads a cell nobody wrote (buffers come from cudaMalloc / the pool and are never cleared).
+    int debug_poison() override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (A.p) CUDA_TRY(cudaMemsetAsync(A.p, 0xFF, A.bytes, stream));
+        if (W.p) CUDA_TRY(cudaMemsetAsync(W.p, 0xFF, W.bytes, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        return HBEGP_OK;
+    }
+
     int debug_factor(double nu, const double* theta, void* k, void* w, void* kinv, int* status) override {
         int nu2, rc;
         if ((rc = nu_to_nu2(nu, &nu2))) return rc;
@@ -710,7 +828,7 @@ struct ModelT : Model {
             k_wmatvec_small<T><<<dim3(nctas, (m + 15) / 16), 256, 0, st>>>((const T*)W.p, np, (const T*)kstar.p, m, psq);
             e->launches++;
         }
-        k_small_finish<T><<<1, 64, 0, st>>>(pmean, ntiles, psq, nctas, m, (T)c, mean, var, nb);
+        k_small_finish<T><<<1, 64, 0, st>>>(pmean, ntiles, psq, nctas, m, (T)c, mean, var, nb, (long*)warn_rows.p, (T*)warn_vals.p, kWarnCap);
         e->launches++;
         CUDA_TRY(cudaGetLastError());
         return HBEGP_OK;
@@ -744,7 +862,7 @@ struct ModelT : Model {
                                                                                        mean, tpc, pm, rows);
                 e->launches++;
                 if (pm) {
-                    k_var_finish<T><<<(rows + 255) / 256, 256, 0, st>>>(nullptr, 0, 0, rows, m, row0, (T)c, nullptr, nb, pm, ns, rows, mean);
+                    k_var_finish<T><<<(rows + 255) / 256, 256, 0, st>>>(nullptr, 0, 0, rows, m, row0, (T)c, nullptr, nb, pm, ns, rows, mean, nullptr, nullptr, 0);
                     e->launches++;
                 }
             }
@@ -779,7 +897,8 @@ struct ModelT : Model {
             g.raster_group = (int)std::max<size_t>(1, ((size_t)48 << 20) / ((size_t)bn * np * sizeof(T)));
             CUDA_TRY((launch_gemm<T, true, true>(g, 1, st)));
             e->launches++;
-            k_var_finish<T><<<(rows + 255) / 256, 256, 0, st>>>((const T*)part.p, ntile, ntile, rows, m, row0, (T)c, var, nb, pm, ns, rows, mean);
+            k_var_finish<T><<<(rows + 255) / 256, 256, 0, st>>>((const T*)part.p, ntile, ntile, rows, m, row0, (T)c, var, nb, pm, ns, rows, mean,
+                                                                (long*)warn_rows.p, (T*)warn_vals.p, kWarnCap);
             e->launches++;
             CUDA_TRY(cudaGetLastError());
         }
@@ -793,6 +912,8 @@ struct ModelT : Model {
         CUDA_TRY(cudaSetDevice(e->device));
         int rc;
         if ((rc = nbelow.ensure(sizeof(unsigned long long)))) return rc;
+        if (var && (rc = warn_rows.ensure(kWarnCap * sizeof(long)))) return rc;
+        if (var && (rc = warn_vals.ensure(kWarnCap * sizeof(T)))) return rc;
         unsigned long long* nb = n_below_device ? (unsigned long long*)n_below_device : (unsigned long long*)nbelow.p;
         if (var) CUDA_TRY(cudaMemsetAsync(nb, 0, sizeof(unsigned long long), e->stream));
         if (nu2 == 5) return predict_impl<5>(m, (const T*)xs, (T*)mean, (T*)var, nb);
@@ -823,6 +944,29 @@ struct ModelT : Model {
         }
         CUDA_TRY(cudaStreamSynchronize(e->stream));
         if (n_below) *n_below = (long)hb;
+        return fetch_warn_list((long)hb);
+    }
+
+    // The (row, value) pairs below the warning level of the prediction that just finished, sorted by row
+    // (the device appends them in arrival order).
+    int fetch_warn_list(long count) {
+        last_warn_vals.clear();
+        last_warn_rows.clear();
+        if (count <= 0) return HBEGP_OK;
+        Engine<T>* e = static_cast<Engine<T>*>(eng);
+        const int k = (int)std::min<long>(count, kWarnCap);
+        std::vector<long> rows(k);
+        std::vector<T> vals(k);
+        CUDA_TRY(cudaMemcpyAsync(rows.data(), warn_rows.p, k * sizeof(long), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaMemcpyAsync(vals.data(), warn_vals.p, k * sizeof(T), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        std::vector<int> order(k);
+        for (int i = 0; i < k; i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return rows[a] < rows[b]; });
+        for (int i : order) {
+            last_warn_rows.push_back(rows[i]);
+            last_warn_vals.push_back((double)vals[i]);
+        }
         return HBEGP_OK;
     }
 };
@@ -876,7 +1020,7 @@ int ModelT<T>::predict_acquisition(int mode, const hbegp_ynorm* yn, long m, cons
     CUDA_TRY(cudaStreamSynchronize(st));
     if (best) *best = hbest;
     if (n_below) *n_below = (long)hb;
-    return HBEGP_OK;
+    return fetch_warn_list((long)hb);
 }
 
 template <typename T>
@@ -889,6 +1033,12 @@ int Engine<T>::model_create(double nu, const double* theta, const double* lo, co
     CUDA_TRY(cudaSetDevice(device));
     if ((rc = ensure_capacity(1))) return rc;
     fill_params(theta, lo, hi, h_prm);
+    {
+        double nz = (double)h_prm[0];  // noise.with_clamped_value(exp(theta_0) rounded through A) (fit.rs:164)
+        if (lo && nz < lo[0]) nz = lo[0];
+        else if (hi && hi[0] < nz) nz = hi[0];
+        next_model_noise = nz;
+    }
     const bool want_kinv = kinv_out != nullptr;
     const double t0 = now_ms();
     if ((rc = run_chunk(nu2, 1, false, want_kinv))) return rc;
@@ -914,6 +1064,7 @@ int Engine<T>::finish_model(int nu2, Model** out, double* lml, void* alpha_out, 
     m->nu2 = nu2;
     m->c = (double)h_prm[1];
     m->prm_h.assign(h_prm, h_prm + p());
+    m->noise_clamped = next_model_noise;
     auto bail = [&](int code) { delete m; return code; };
     if ((rc = m->W.ensure((size_t)np * np * sizeof(T)))) return bail(rc);
     if ((rc = m->alpha.ensure((size_t)np * sizeof(T)))) return bail(rc);
@@ -1004,11 +1155,15 @@ int Engine<T>::model_extend(Model* prior_, Model** out, double* lml, void* alpha
     CUDA_TRY(cudaSetDevice(device));
     if ((rc = ensure_capacity(1))) return rc;
     for (int k = 0; k < p(); k++) h_prm[k] = (T)prior->prm_h[k];
+    h_prm[0] = (T)prior->noise_clamped;  // extend evaluates with prior.noise, the CLAMPED value (fit.rs:41-44, gpr.rs:322)
+    next_model_noise = prior->noise_clamped;
+    // an append reuses the prior factor, which is only valid if it was computed with the same noise
+    const bool same_noise = (T)prior->noise_clamped == (T)prior->prm_h[0];
     const int nu2 = prior->nu2;
     const bool want_kinv = kinv_out != nullptr;
     // the append needs at least one complete 64-row leaf of the prior model and the old rows as a prefix
     int r1 = (int)(std::min<long>(prior->n, n) / TILE) * TILE;
-    if (prior->n > n) r1 = 0;
+    if (prior->n > n || !same_noise) r1 = 0;
     if (r1 > 0) {
         CUDA_TRY(cudaMemcpyAsync(prm.p, h_prm, (size_t)p() * sizeof(T), cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemsetAsync(d_status.p, 0, sizeof(int), stream));
@@ -1242,8 +1397,12 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
     int nsub = 4;
     bool forced = false;
     if (const char* s = getenv("HBEGP_STREAMS")) { nsub = std::max(1, std::min(16, atoi(s))); forced = true; }
-    if (const char* s = getenv("HBEGP_TILE")) gemm_tile_pref() = (atoi(s) == 128) ? 128 : 64;
-    if (const char* s = getenv("HBEGP_TILE32")) gemm_tile_pref_f32() = (atoi(s) == 128) ? 128 : 64;
+    {
+        const char* s64 = getenv("HBEGP_TILE");
+        const char* s32 = getenv("HBEGP_TILE32");
+        gemm_tile_pref() = (s64 && atoi(s64) == 128) ? 128 : 64;
+        gemm_tile_pref_f32() = (s32 && atoi(s32) == 128) ? 128 : 64;
+    }
     bool graphs_on = true;
     if (const char* s = getenv("HBEGP_GRAPHS")) graphs_on = atoi(s) != 0;
     if (dtype == HBEGP_F64) { static_cast<Engine<double>*>(e)->streams_forced = forced; static_cast<Engine<double>*>(e)->use_graphs = graphs_on; }
@@ -1412,8 +1571,52 @@ int hbegp_model_destroy(hbegp_model* model) {
     return HBEGP_OK;
 }
 
-long hbegp_model_n(const hbegp_model* model) { return model ? model->m->n : 0; }
-int hbegp_model_dim(const hbegp_model* model) { return model ? model->m->d : 0; }
+long hbegp_model_n(const hbegp_model* model) { return (model && model->m) ? model->m->n : 0; }
+int hbegp_model_dim(const hbegp_model* model) { return (model && model->m) ? model->m->d : 0; }
+
+int hbegp_predict_warn_values(const hbegp_model* model, int cap, double* values_out, long* rows_out) {
+    if (!model || !model->m || cap < 0 || (cap > 0 && !values_out)) return fail(HBEGP_ERR_INVALID, "predict_warn_values: bad arguments");
+    const int k = (int)std::min<size_t>((size_t)cap, model->m->last_warn_vals.size());
+    for (int i = 0; i < k; i++) {
+        values_out[i] = model->m->last_warn_vals[i];
+        if (rows_out) rows_out[i] = model->m->last_warn_rows[i];
+    }
+    return k;
+}
+
+int hbegp_kernel_matrix(hbegp_ctx* ctx, double nu, int d, const double* theta, long n1, const void* x1, long n2, const void* x2,
+                        void* k_out) {
+    if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");
+    return ctx->eng->kernel_matrix(nu, d, theta, n1, x1, n2, x2, k_out);
+}
+
+int hbegp_kernel_theta_grad(hbegp_ctx* ctx, double nu, int d, const double* theta, long n, const void* x, void* k_out,
+                            void* grad_out) {
+    if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");
+    return ctx->eng->kernel_theta_grad(nu, d, theta, n, x, k_out, grad_out);
+}
+
+int hbegp_kernel_diag(int dtype, int d, const double* theta, long n, void* diag_out) {
+    // Product<ConstantKernel, Matern>::diag = c * 1 (product_kernel.rs:72-74, constant_kernel.rs:40-42,
+    // matern_kernel.rs:137-139); no device work
+    if (d <= 0 || !theta || n < 0 || (n > 0 && !diag_out)) return fail(HBEGP_ERR_INVALID, "kernel_diag: bad arguments");
+    if (dtype == HBEGP_F64) {
+        const double c = std::exp(theta[0]);
+        for (long i = 0; i < n; i++) ((double*)diag_out)[i] = c * 1.0;
+    } else if (dtype == HBEGP_F32) {
+        const float c = (float)std::exp(theta[0]);
+        for (long i = 0; i < n; i++) ((float*)diag_out)[i] = c * 1.0f;
+    } else {
+        return fail(HBEGP_ERR_INVALID, "kernel_diag: bad dtype");
+    }
+    return HBEGP_OK;
+}
+
+int hbegp_lbfgs_set_tolerances(double ftol, double gtol) {
+    lbfgs_tolerances().ftol = ftol;
+    lbfgs_tolerances().gtol = gtol;
+    return HBEGP_OK;
+}
 
 int hbegp_predict(hbegp_model* model, long m, const void* xs, void* mean, void* var, long* n_below_warn) {
     if (!model) return fail(HBEGP_ERR_INVALID, "null model");
@@ -1521,6 +1724,11 @@ int hbegp_bench_phase(hbegp_ctx* ctx, double nu, int B, const double* theta, int
     if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");
     if (ctx->eng->n <= 0) return fail(HBEGP_ERR_INVALID, "no training data: call hbegp_set_data first");
     return ctx->eng->bench_phase(nu, B, theta, phase, reps, ms_out);
+}
+
+int hbegp_debug_poison(hbegp_ctx* ctx) {
+    if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");
+    return ctx->eng->debug_poison();
 }
 
 int hbegp_debug_factor(hbegp_ctx* ctx, double nu, const double* theta, void* k, void* w, void* kinv, int* status) {

@@ -11,6 +11,11 @@ namespace hbegp {
 
 constexpr int TILE = 64;  // leaf / tile edge
 
+// `ulps_eq!(std, 0.0)` of expected_improvement (src/core/acquisition.rs:148): approx 0.3 tests abs_diff_eq with
+// epsilon = f64::EPSILON first, so any |std| <= 2.2e-16 takes the trivial branch (the ULP test that follows can only
+// add denormals, which the first test already covers).  Shared by the host adapter and k_acquisition.
+__host__ __device__ inline bool ei_std_is_zero(double sd) { return sd <= 0.0 || fabs(sd) <= 2.220446049250313e-16; }
+
 // Per-evaluation hyper-parameters, already clamped and rounded to T on the host
 // (src/gpr/fit.rs:94-96): prm[0] = noise, prm[1] = c, prm[2 + k] = l_k.
 template <typename T>
@@ -42,6 +47,28 @@ __device__ __forceinline__ T matern_corr(T r) {
     }
     T k = r * T(2.2360679774997896964);
     return (T(1) + k + k * k / T(3)) * dev_exp<T>(-k);
+}
+
+// Per-entry terms of the theta gradient (src/gpr/matern_kernel.rs:83-135) from s = sum_k d_ijk,
+// d_ijk = (x_ik - x_jk)^2 / l_k^2: kval = the correlation recomputed from t = sqrt(2 nu s), and dk_factor such that
+// dM_ij / d ln l_k = dk_factor * d_ijk.
+template <typename T, int NU2>
+__device__ __forceinline__ void matern_grad_terms(T s, T& kval, T& dk_factor) {
+    if (NU2 == 5) {
+        const T t = dev_sqrt<T>(T(5) * s);
+        const T e = dev_exp<T>(-t);
+        kval = (T(1) + t + t * t / T(3)) * e;
+        dk_factor = e * (t + T(1)) * T(5.0 / 3.0);  // matern_kernel.rs:120-130
+    } else if (NU2 == 3) {
+        const T t = dev_sqrt<T>(T(3) * s);
+        const T e = dev_exp<T>(-t);
+        kval = (t + T(1)) * e;
+        dk_factor = T(3) * e;  // matern_kernel.rs:112-118
+    } else {
+        const T r = dev_sqrt<T>(s);
+        kval = dev_exp<T>(-r);
+        dk_factor = (r > T(0)) ? kval / r : T(0);  // matern_kernel.rs:102-111 (non-finite -> 0)
+    }
 }
 
 // lower-triangle tile enumeration: t -> (mt >= nt)
@@ -435,6 +462,7 @@ __global__ void __launch_bounds__(256) k_node128(T* __restrict__ A, T* __restric
         for (int q = 0; q < 4; q++) {
             const int i = ty + 16 * a, k = tx + 16 * q;
             Wb[(long)i * np + k] = (k <= i) ? w1[i][k] : T(0);
+            Wb[(long)i * np + TILE + k] = T(0);  // (0,1) block: read by the 128-wide GEMM tiles' triangular k ranges
             Wb[(long)(i + TILE) * np + k] = -acc[a][q];
             Wb[(long)(i + TILE) * np + TILE + k] = (k <= i) ? w2[i][k] : T(0);
         }
@@ -562,21 +590,7 @@ __global__ void __launch_bounds__(256) k_grad_contract(const T* __restrict__ Kin
                 const T tij = ai[li] * aj[lj] - kv[a * 4 + q];
                 const T s = S[a * 4 + q];
                 T base, dk_factor, kval;
-                if (NU2 == 5) {
-                    const T t = dev_sqrt<T>(T(5) * s);
-                    const T e = dev_exp<T>(-t);
-                    kval = (T(1) + t + t * t / T(3)) * e;
-                    dk_factor = e * (t + T(1)) * T(5.0 / 3.0);  // matern_kernel.rs:120-130
-                } else if (NU2 == 3) {
-                    const T t = dev_sqrt<T>(T(3) * s);
-                    const T e = dev_exp<T>(-t);
-                    kval = (t + T(1)) * e;
-                    dk_factor = T(3) * e;  // matern_kernel.rs:112-118
-                } else {
-                    const T r = dev_sqrt<T>(s);
-                    kval = dev_exp<T>(-r);
-                    dk_factor = (r > T(0)) ? kval / r : T(0);  // matern_kernel.rs:102-111 (non-finite -> 0)
-                }
+                matern_grad_terms<T, NU2>(s, kval, dk_factor);
                 base = wgt * tij * c;
                 cm[a * 4 + q] = base * dk_factor;
                 g_c += (double)(base * kval);
@@ -826,10 +840,22 @@ __global__ void __launch_bounds__(256) k_wmatvec_small(const T* __restrict__ W, 
     }
 }
 
+// A variance below the warning level -sqrt(1e-5) (predict.rs:39-46, :104-127): counted, and the first `warn_cap`
+// (row, value) pairs that arrive are kept so that the host can list them like the reference's stderr message.
+template <typename T>
+__device__ __forceinline__ void note_below(unsigned long long* n_below, long* warn_rows, T* warn_vals, int warn_cap, long row, T v) {
+    const unsigned long long slot = atomicAdd(n_below, 1ULL);
+    if (warn_rows != nullptr && slot < (unsigned long long)warn_cap) {
+        warn_rows[slot] = row;
+        warn_vals[slot] = v;
+    }
+}
+
 // mean[r] = sum_tiles pmean[tile][r]; var[r] = c + 1e-5 - sum_ctas psq[cta][r] (counted / clamped like k_var_finish)
 template <typename T>
 __global__ void k_small_finish(const T* __restrict__ pmean, int ntiles, const T* __restrict__ psq, int nctas, int m, T c,
-                               T* __restrict__ mean, T* __restrict__ var, unsigned long long* __restrict__ n_below) {
+                               T* __restrict__ mean, T* __restrict__ var, unsigned long long* __restrict__ n_below,
+                               long* __restrict__ warn_rows, T* __restrict__ warn_vals, int warn_cap) {
     const int r = threadIdx.x;
     if (r >= m) return;
     T s = T(0);
@@ -840,7 +866,7 @@ __global__ void k_small_finish(const T* __restrict__ pmean, int ntiles, const T*
     for (int t = 0; t < nctas; t++) q += psq[(long)t * 64 + r];
     const T min_noise = T(1e-5);
     T v = c + min_noise - q;
-    if (v < -dev_sqrt<T>(min_noise)) atomicAdd(n_below, 1ULL);
+    if (v < -dev_sqrt<T>(min_noise)) note_below<T>(n_below, warn_rows, warn_vals, warn_cap, r, v);
     if (v < T(0)) v = T(0);
     var[r] = v;
 }
@@ -850,7 +876,8 @@ __global__ void k_small_finish(const T* __restrict__ pmean, int ntiles, const T*
 template <typename T>
 __global__ void k_var_finish(const T* __restrict__ part, int ld, int ntiles, long rows, long m, long row0, T c,
                              T* __restrict__ var, unsigned long long* __restrict__ n_below,
-                             const T* __restrict__ pmean, int nsplit, long pm_stride, T* __restrict__ mean) {
+                             const T* __restrict__ pmean, int nsplit, long pm_stride, T* __restrict__ mean,
+                             long* __restrict__ warn_rows, T* __restrict__ warn_vals, int warn_cap) {
     long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows || row0 + r >= m) return;
     if (pmean != nullptr) {  // mean partials of the column-split k* kernel, summed in split order
@@ -863,7 +890,7 @@ __global__ void k_var_finish(const T* __restrict__ part, int ld, int ntiles, lon
     for (int t = 0; t < ntiles; t++) s += part[r * ld + t];
     const T min_noise = T(1e-5);
     T v = c + min_noise - s;
-    if (v < -dev_sqrt<T>(min_noise)) atomicAdd(n_below, 1ULL);
+    if (v < -dev_sqrt<T>(min_noise)) note_below<T>(n_below, warn_rows, warn_vals, warn_cap, row0 + r, v);
     if (v < T(0)) v = T(0);
     var[row0 + r] = v;
 }
@@ -901,7 +928,7 @@ __global__ void k_acquisition(const T* __restrict__ mean, const T* __restrict__ 
     if (mode == 0) {
         const double mean_d = (double)mu, std_d = (double)sd;
         double ei;
-        if (std_d <= 0.0 || fabs(std_d) < 4 * 2.2250738585072014e-308) {
+        if (ei_std_is_zero(std_d)) {
             ei = mean_d < fmin_n ? -(mean_d - fmin_n) : 0.0;
         } else {
             const double z = -(mean_d - fmin_n) / std_d;
@@ -986,6 +1013,50 @@ __global__ void k_sym_fill(const T* __restrict__ in, int np, int n, T* __restric
     if (mode == 0) v = (i >= j) ? in[(long)i * np + j] : in[(long)j * np + i];  // symmetric
     else v = (i >= j) ? in[(long)i * np + j] : T(0);                             // lower only
     out[(long)i * n + j] = v;
+}
+
+// ---- standalone kernel evaluation (trait Kernel, src/gpr/kernel.rs:8-43) for parity checks against the reference's
+// golden vectors.  The hot path never materialises the (n, n, d+1) tensor; this kernel writes it with exactly the
+// per-entry terms k_grad_contract contracts (matern_grad_terms), for Product<ConstantKernel, Matern>:
+//   k_out[i][j] = c * matern(|x_i / l - x_j / l|)                        (matern_kernel.rs:37-80, product_kernel.rs:36-38)
+//   grad[i][j][0] = c * M_ij, grad[i][j][1 + k] = dM_ij / d ln l_k * c    (product_kernel.rs:40-70)
+template <typename T, int NU2>
+__global__ void k_kernel_theta_grad(const T* __restrict__ x, int n, int d, const T* __restrict__ ls, T c,
+                                    T* __restrict__ k_out, T* __restrict__ grad) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= n || i >= n) return;
+    T r2 = T(0);
+    for (int k = 0; k < d; k++) {
+        const T df = x[(long)i * d + k] / ls[k] - x[(long)j * d + k] / ls[k];  // division first (matern_kernel.rs:51-60)
+        r2 += df * df;
+    }
+    const T kij = c * matern_corr<T, NU2>(dev_sqrt<T>(r2));
+    if (k_out) k_out[(long)i * n + j] = kij;
+    if (!grad) return;
+    // like k_grad_contract, d_ijk is formed from the scaled inputs ((x_ik / l_k - x_jk / l_k)^2; the reference squares
+    // the raw difference and then divides by l_k^2, matern_kernel.rs:95-98 -- equal up to rounding)
+    T kval, dk_factor;
+    matern_grad_terms<T, NU2>(r2, kval, dk_factor);
+    T* g = grad + ((long)i * n + j) * (d + 1);
+    g[0] = c * kval;  // constant_kernel.rs:31-38 times k2.kernel
+    for (int k = 0; k < d; k++) {
+        const T df = x[(long)i * d + k] / ls[k] - x[(long)j * d + k] / ls[k];
+        g[1 + k] = dk_factor * (df * df) * c;
+    }
+}
+
+template <typename T>
+__global__ void k_fill(T* __restrict__ out, long n, T v) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
+// out[i][j] = in[i * ld + j] for j < cols (drops the column padding of a k* chunk)
+template <typename T>
+__global__ void k_copy_cols(const T* __restrict__ in, long ld, long rows, int cols, T* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const long i = blockIdx.y;
+    if (j < cols && i < rows) out[i * cols + j] = in[i * ld + j];
 }
 
 }  // namespace hbegp

@@ -19,11 +19,23 @@
 
 namespace hbegp {
 
+// Stopping tolerances of every BoundedLbfgs created afterwards (process-wide; hbegp_lbfgs_set_tolerances).  The
+// reference sets only maxeval on NLopt (gradmin.rs:52-54); NLopt's own L-BFGS still stops on a stalled objective
+// (Luksan PLIS: two consecutive iterations without progress) and on a vanishing gradient, which these defaults stand
+// in for.  A value <= 0 switches the rule off (maxeval-only stopping).
+struct LbfgsTolerances {
+    double ftol = 1e-11, gtol = 1e-8;
+};
+inline LbfgsTolerances& lbfgs_tolerances() {
+    static LbfgsTolerances t;
+    return t;
+}
+
 class BoundedLbfgs {
 public:
     BoundedLbfgs(int n, const double* x0, const double* lo, const double* hi, int maxeval, int memory = 10)
         : n_(n), m_(memory), maxeval_(maxeval), lo_(lo, lo + n), hi_(hi, hi + n), x_(n), g_(n), xt_(x0, x0 + n),
-          d_(n), free_(n, 1) {
+          d_(n), free_(n, 1), ftol_(lbfgs_tolerances().ftol), gtol_(lbfgs_tolerances().gtol) {
         for (int i = 0; i < n_; i++) xt_[i] = std::min(std::max(xt_[i], lo_[i]), hi_[i]);
         done_ = (maxeval_ <= 0);
     }
@@ -52,6 +64,17 @@ public:
         // line-search trial
         double dec = 0.0;  // g . (xt - x)
         for (int i = 0; i < n_; i++) dec += g_[i] * (xt_[i] - x_[i]);
+        if (!(dec < 0.0)) {
+            // the projection bent the quasi-Newton step into a non-descent displacement: Armijo and the quadratic
+            // interpolation below both assume a negative slope, so this is a failed direction, not a trial to judge
+            if (!S_.empty() || !steepest_) {
+                S_.clear();
+                Y_.clear();
+                rho_.clear();
+                return next_direction(true);
+            }
+            return finish();
+        }
         if (finite && ft <= f_ + c1_ * dec) {
             // accept
             std::vector<double> s(n_), y(n_);
@@ -78,7 +101,7 @@ public:
             f_ = ft;
             g_.assign(gt, gt + n_);
             const double scale = std::max(std::max(std::fabs(fprev), std::fabs(f_)), 1.0);
-            if (fprev - f_ <= ftol_ * scale) stall_++;
+            if (ftol_ > 0 && fprev - f_ <= ftol_ * scale) stall_++;
             else stall_ = 0;
             if (stall_ >= 2) return finish();
             return next_direction(false);
@@ -127,7 +150,7 @@ private:
                 pgmax = std::max(pgmax, std::fabs(g_[i]));
             }
         }
-        if (nfree == 0 || pgmax <= gtol_) return finish();
+        if (nfree == 0 || pgmax <= (gtol_ > 0 ? gtol_ : 0.0)) return finish();
         steepest_ = force_steepest || S_.empty();
         // two-loop recursion on the free variables
         std::vector<double> q(n_);
@@ -213,7 +236,8 @@ private:
     std::vector<double> rho_;
     double f_ = std::numeric_limits<double>::infinity();
     double alpha_ = 1.0;
-    const double c1_ = 1e-4, ftol_ = 1e-11, gtol_ = 1e-8;
+    const double c1_ = 1e-4;
+    double ftol_, gtol_;
     int evals_ = 0, ls_iter_ = 0, stall_ = 0;
     bool have_x_ = false, done_ = false, steepest_ = true;
 };

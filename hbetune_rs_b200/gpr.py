@@ -131,6 +131,38 @@ class Product:
     def natural_bounds(self):
         return self.k1.natural_bounds() + self.k2.natural_bounds()
 
+    # ---- trait Kernel evaluation (src/gpr/kernel.rs:8-43), on the GPU through the C ABI
+    def kernel(self, ctx: "Context", x1, x2) -> np.ndarray:
+        """``Kernel::kernel(x1, x2) -> (n1, n2)`` (``kernel.rs:10-14``, ``product_kernel.rs:36-38``)."""
+        x1 = np.ascontiguousarray(x1, dtype=ctx.A)
+        x2 = np.ascontiguousarray(x2, dtype=ctx.A)
+        assert x1.ndim == 2 and x2.ndim == 2 and x1.shape[1] == x2.shape[1] == self.k2.n_params()
+        out = np.empty((x1.shape[0], x2.shape[0]), dtype=ctx.A)
+        theta = np.array(self.theta(), dtype=np.float64)
+        check(lib.hbegp_kernel_matrix(ctx._h, self.k2.nu, x1.shape[1], _ptr(theta), x1.shape[0], _ptr(x1), x2.shape[0],
+                                      _ptr(x2), _ptr(out)), "hbegp_kernel_matrix")
+        return out
+
+    def theta_grad(self, ctx: "Context", x) -> Tuple[np.ndarray, np.ndarray]:
+        """``Kernel::theta_grad(x) -> ((n, n), (n, n, n_params))`` (``kernel.rs:16-21``, ``product_kernel.rs:40-70``)."""
+        x = np.ascontiguousarray(x, dtype=ctx.A)
+        n, d = x.shape
+        assert d == self.k2.n_params()
+        k = np.empty((n, n), dtype=ctx.A)
+        g = np.empty((n, n, d + 1), dtype=ctx.A)
+        theta = np.array(self.theta(), dtype=np.float64)
+        check(lib.hbegp_kernel_theta_grad(ctx._h, self.k2.nu, d, _ptr(theta), n, _ptr(x), _ptr(k), _ptr(g)),
+              "hbegp_kernel_theta_grad")
+        return k, g
+
+    def diag(self, ctx: "Context", x) -> np.ndarray:
+        """``Kernel::diag(x) -> (n)`` (``kernel.rs:23-24``, ``product_kernel.rs:72-74``)."""
+        n = np.asarray(x).shape[0]
+        out = np.empty(n, dtype=ctx.A)
+        theta = np.array(self.theta(), dtype=np.float64)
+        check(lib.hbegp_kernel_diag(ctx.dtype, self.k2.n_params(), _ptr(theta), n, _ptr(out)), "hbegp_kernel_diag")
+        return out
+
 
 def _np_dtype(dtype: int):
     return np.float64 if dtype == _lib.F64 else np.float32
@@ -226,6 +258,9 @@ class Context:
         check(lib.hbegp_bench_phase(self._h, nu, theta.shape[0], _ptr(theta), phase, reps, C.byref(ms)), "hbegp_bench_phase")
         return float(ms.value)
 
+    def debug_poison(self):
+        check(lib.hbegp_debug_poison(self._h), "hbegp_debug_poison")
+
     def debug_factor(self, theta, nu: float = 2.5, want=("k", "w", "kinv")):
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         out = {k: (np.empty((self.n, self.n), dtype=self.A) if k in want else None) for k in ("k", "w", "kinv")}
@@ -287,11 +322,22 @@ class Model:
         var = np.empty(m, dtype=self.A) if want_variance else None
         nb = C.c_long(0)
         check(lib.hbegp_predict(self._h, m, _ptr(xs), _ptr(mean), _ptr(var), C.byref(nb)), "hbegp_predict")
-        if warn and nb.value:
-            # predict.rs:39-46 prints the offending values; the device path reports their count
-            print(f"Variances below 0 were predicted and will be corrected: {nb.value} value(s)", file=sys.stderr)
         self.n_below_warn = nb.value
+        if warn and nb.value:
+            # predict.rs:39-46 lists the offending values with {:.2e}
+            vals, _ = self.warn_values()
+            more = "" if len(vals) == nb.value else f", ... ({nb.value} in all)"
+            print("Variances below 0 were predicted and will be corrected: "
+                  + ", ".join(f"{v:.2e}" for v in vals) + more, file=sys.stderr)
         return mean, var
+
+    def warn_values(self, cap: int = 16):
+        """The pre-clamp variances below -sqrt(1e-5) of the last prediction, in row order, with their rows
+        (``hbegp_predict_warn_values``; ``predict.rs:39-46``, ``:104-127``)."""
+        vals = np.empty(cap)
+        rows = np.empty(cap, dtype=np.int64)
+        k = check(lib.hbegp_predict_warn_values(self._h, cap, _ptr(vals), _ptr(rows)), "hbegp_predict_warn_values")
+        return vals[:k], rows[:k]
 
     def predict_device(self, m: int, xs_ptr: int, mean_ptr: int, var_ptr: Optional[int] = None):
         check(lib.hbegp_predict_device(self._h, m, C.c_void_p(xs_ptr), C.c_void_p(mean_ptr),

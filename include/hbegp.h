@@ -141,6 +141,11 @@ int hbegp_model_dim(const hbegp_model* model);
  * below 0 clamped to 0; *n_below_warn (may be NULL) counts values < -sqrt(1e-5) BEFORE clamping, i.e. the
  * entries the reference lists in its stderr warning (predict.rs:39-46). */
 int hbegp_predict(hbegp_model* model, long m, const void* xs, void* mean, void* var, long* n_below_warn);
+/* The values the reference lists in its warning ("Variances below 0 were predicted and will be corrected: ...",
+ * src/gpr/predict.rs:39-46): the pre-clamp variances < -sqrt(1e-5) of the LAST hbegp_predict / hbegp_predict_mean_ei /
+ * hbegp_predict_confidence_bound call on this model, in row order, with their row indices (rows_out may be NULL).
+ * Returns how many were written (<= cap; the library keeps at most 4096 per call, n_below_warn has the full count). */
+int hbegp_predict_warn_values(const hbegp_model* model, int cap, double* values_out, long* rows_out);
 /* Same with device-resident candidates and outputs (asynchronous on the context's stream). */
 int hbegp_predict_device(hbegp_model* model, long m, const void* xs_device, void* mean_device,
                          void* var_device, long* n_below_warn_device);
@@ -167,6 +172,12 @@ int hbegp_predict_confidence_bound(hbegp_model* model, const struct hbegp_ynorm*
 typedef double (*hbegp_objective_fn)(const double* x, double* grad_out, void* user);
 int hbegp_minimize_by_gradient(hbegp_objective_fn objective, void* user, int n, double* x,
                                const double* lo, const double* hi, int maxeval, double* f_out);
+
+/* Stopping tolerances of the bounded L-BFGS for every run started afterwards (process-wide).  Defaults ftol = 1e-11
+ * (two consecutive accepted steps with a relative decrease below it end a run) and gtol = 1e-8 (largest free gradient
+ * component); a value <= 0 switches that rule off, leaving maxeval as the only stop like the reference's NLopt
+ * configuration (src/util/gradmin.rs:52-54). */
+int hbegp_lbfgs_set_tolerances(double ftol, double gtol);
 
 /* Xoshiro256** restart-start sampler: src/core/random.rs + src/util/gradmin.rs:21-24.  `state[4]` is the
  * generator state (updated).  hbegp_rng_seed = RNG::new_with_seed, hbegp_rng_fork = fork_random_state,
@@ -203,12 +214,31 @@ int hbegp_expected_improvement_a(int dtype, long m, const void* mean, const void
 /* statrs Normal::inverse_cdf as used for the quartiles of predict_statistics (src/core/gpr.rs:140-166). */
 double hbegp_normal_inverse_cdf(double p, double mean, double std);
 
+/* ---- trait Kernel, standalone (src/gpr/kernel.rs:8-43) -------------------------------------------- */
+/* For Product<ConstantKernel, Matern(nu)> with theta = [ln c, ln l_1 .. ln l_d] (kernel.theta(), product_kernel.rs:80-85;
+ * no noise term, no clamping).  A plain Matern kernel (the reference's golden vectors matern_kernel.rs:189-253) is the
+ * case ln c = 0.  The context supplies device, data type and stream; its training data is not touched.
+ *   hbegp_kernel_matrix:      Kernel::kernel(x1 (n1 x d), x2 (n2 x d)) -> k_out (n1 x n2)   (kernel.rs:10-14), computed by the
+ *                             production cross-kernel code (the k* tiles of predict);
+ *   hbegp_kernel_theta_grad:  Kernel::theta_grad(x (n x d)) -> k_out (n x n), grad_out (n x n x (d + 1)), slice 0 =
+ *                             d/d ln c, slices 1..d = d/d ln l_k (kernel.rs:16-21, product_kernel.rs:40-70); either may be NULL;
+ *   hbegp_kernel_diag:        Kernel::diag(x) -> diag_out (n) = c (kernel.rs:23-24); host-only. */
+int hbegp_kernel_matrix(hbegp_ctx* ctx, double nu, int d, const double* theta, long n1, const void* x1, long n2,
+                        const void* x2, void* k_out);
+int hbegp_kernel_theta_grad(hbegp_ctx* ctx, double nu, int d, const double* theta, long n, const void* x, void* k_out,
+                            void* grad_out);
+int hbegp_kernel_diag(int dtype, int d, const double* theta, long n, void* diag_out);
+
 /* ---- debugging / parity aids -------------------------------------------------------------------- */
 /* Copies out intermediates of ONE evaluation at theta (any pointer may be NULL): k[n*n] lower triangle of
  * K + noise I (upper = 0), w[n*n] = L^-1 (the inverse Cholesky factor; L itself is consumed by the fused
  * factor-and-invert recursion), kinv[n*n] full symmetric. */
 int hbegp_debug_factor(hbegp_ctx* ctx, double nu, const double* theta, void* k, void* w, void* kinv,
                        int* status);
+
+/* Overwrites the context's batched evaluation workspaces with NaN bit patterns (test aid: results must not depend on
+ * what a previous evaluation or allocation left behind). */
+int hbegp_debug_poison(hbegp_ctx* ctx);
 
 /* Times (CUDA events on the context's stream, average of `reps` after one warm-up) a truncated batched
  * evaluation of B thetas: phase 0 = kernel-matrix assembly, 1 = + factor/inverse recursion, 2 = + alpha and

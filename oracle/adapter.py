@@ -121,7 +121,8 @@ def _norm_pdf(z: float) -> float:
 def expected_improvement(mean: float, std: float, fmin: float) -> float:
     """``src/core/acquisition.rs:141-171`` (f64)."""
     assert math.isfinite(mean) and math.isfinite(std) and math.isfinite(fmin)
-    if std <= 0.0 or abs(std) < 4 * 2.2250738585072014e-308:  # `ulps_eq!(std, 0.0)`
+    # `ulps_eq!(std, 0.0)` (approx 0.3): abs_diff_eq with epsilon = f64::EPSILON comes first, then <= 4 ULPs
+    if std <= 0.0 or abs(std) <= 2.220446049250313e-16:
         return -(mean - fmin) if mean < fmin else 0.0
     z = -(mean - fmin) / std
     ei = -(mean - fmin) * _norm_cdf(z) + std * _norm_pdf(z)

@@ -1,0 +1,319 @@
+"""The BASELINE.json configurations under DIRECT oracle comparison ("next round" item 1):
+
+  (a) C3   n = 1024, d = 8: all 33 thetas of the bench batch, f64 at 1e-9 and f32 at 1e-4 against the oracle in the
+           same precision: LML, gradient, and mean / variance of 1,000 candidates;
+  (b) NS   n = 4096, d = 16: one theta against the oracle, f64 and f32;
+  (c) C4   2^20 candidates on the n = 4096 model, compared on > 1,000 sampled rows (chunk edges included) with a
+           prediction the oracle makes from ITS OWN alpha and K^-1;
+  (d) C5   n = 16384, d = 32: one theta against a lean host evaluation (potrf, no (n, n, d+1) tensor -- the
+           reference-faithful form needs 70.9 GB at this shape) plus alpha and K^-1 on sampled columns;
+  (e) the CUDA kernel evaluation straight against the reference-held golden blocks
+      (src/gpr/matern_kernel.rs:189-253, src/gpr/product_kernel.rs:120-169) through hbegp_kernel_matrix /
+      hbegp_kernel_theta_grad (trait Kernel, src/gpr/kernel.rs:8-43);
+  (f) the f32 north-star optimum: the f32 oracle and the f32 CUDA path evaluated at the f64-fitted and at the
+      f32-fitted theta (profiles/r01_bench_ns_f32.json reported different optima without saying why).
+
+Tolerances: BASELINE north_star (f64 1e-9, f32 1e-4, relative); variances as |d var| <= tol * (c + 1e-5).
+"""
+import argparse
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+from scipy.linalg import lapack
+
+from oracle import gpr as ogpr
+from tests.util import oracle_kernel, oracle_lml, random_thetas, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float64: 1e-9, np.float32: 1e-4}
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ctx(A):
+    import hbetune_rs_b200 as h
+    return h.Context(0, h.F64 if A == np.float64 else h.F32)
+
+
+def _note(name, payload):
+    """Leaves the measured differences under gpurun_out/ (scratch) so that a run's numbers can be read afterwards."""
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", name), "w") as f:
+            json.dump(payload, f, indent=1)
+    except OSError:
+        pass
+
+
+def _bench_workload(n, d, restarts, dtype):
+    import bench
+    args = argparse.Namespace(n=n, d=d, restarts=restarts, m=8, dtype=dtype)
+    return bench.workload(args)
+
+
+# ------------------------------------------------------------------------------------------------ (e)
+def _goldens():
+    with open(os.path.join(ROOT, "tests", "golden", "reference_kernel_goldens.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("A,tol", [(np.float64, 6e-9), (np.float32, 3e-7)])
+@pytest.mark.parametrize("block,nu", [("matern_nu_1_5", 1.5), ("matern_nu_2_5", 2.5), ("product_constant2_matern_2_5", 2.5)])
+def test_cuda_kernel_against_the_reference_goldens(block, nu, A, tol):
+    import hbetune_rs_b200 as h
+    g = _goldens()[block]
+    x = np.array(g["x"], dtype=A)
+    c = float(g.get("constant", 1.0))
+    bv = h.BoundedValue
+    kernel = h.Product(h.ConstantKernel(bv(c, 1.0, 5.0)), h.Matern(nu, [bv(l, 0.05, 20.0) for l in g["length_scale"]]))
+    km, gm = np.array(g["kernel"]), np.array(g["gradient"])
+    with _ctx(A) as ctx:
+        k = kernel.kernel(ctx, x, x)
+        k2, grad = kernel.theta_grad(ctx, x)
+        diag = kernel.diag(ctx, x)
+    assert k.dtype == A and grad.dtype == A
+    scale = max(1.0, c)
+    np.testing.assert_allclose(k, km, rtol=0, atol=tol * scale)
+    np.testing.assert_allclose(k2, km, rtol=0, atol=tol * scale)
+    if "constant" in g:
+        np.testing.assert_allclose(grad, gm, rtol=0, atol=tol * scale)
+    else:  # plain Matern golden: slice 0 of the product gradient is d/d ln c = K itself
+        np.testing.assert_allclose(grad[:, :, 1:], gm, rtol=0, atol=tol)
+        np.testing.assert_allclose(grad[:, :, 0], km, rtol=0, atol=tol)
+    np.testing.assert_allclose(diag, np.diag(km), rtol=0, atol=1e-7 * scale)
+
+
+@pytest.mark.parametrize("A", [np.float64, np.float32])
+@pytest.mark.parametrize("n1,n2,d,nu", [(1, 1, 1, 2.5), (5, 130, 3, 2.5), (200, 64, 8, 1.5), (4500, 70, 2, 0.5), (65, 65, 16, 2.5)])
+def test_cuda_kernel_matrix_and_gradient_against_the_oracle(n1, n2, d, nu, A):
+    import hbetune_rs_b200 as h
+    rng = np.random.default_rng(n1 + 7 * n2)
+    x1, x2 = rng.random((n1, d)).astype(A), rng.random((n2, d)).astype(A)
+    theta = random_thetas(1, d, seed=n1)[0]
+    ok = oracle_kernel(theta, nu)
+    bv = h.BoundedValue
+    kernel = h.Product(h.ConstantKernel(bv(math.exp(theta[1]), 1e-9, 1e9)),
+                       h.Matern(nu, [bv(math.exp(t), 1e-9, 1e9) for t in theta[2:]]))
+    tol = 1e-12 if A == np.float64 else 2e-6
+    c = math.exp(theta[1])
+    with _ctx(A) as ctx:
+        k = kernel.kernel(ctx, x1, x2)
+        np.testing.assert_allclose(k, ok.kernel(x1, x2, A), rtol=0, atol=tol * c)
+        if n2 <= 200:
+            k_sq, grad = kernel.theta_grad(ctx, x2)
+            k_ref, g_ref = ok.theta_grad(x2, A)
+            np.testing.assert_allclose(k_sq, k_ref, rtol=0, atol=tol * c)
+            np.testing.assert_allclose(grad, g_ref, rtol=0, atol=10 * tol * max(1.0, np.abs(g_ref).max()))
+
+
+# ------------------------------------------------------------------------------------------------ (a)
+@pytest.mark.parametrize("A,dtype", [(np.float64, "f64"), (np.float32, "f32")])
+def test_c3_bench_batch_against_the_oracle(A, dtype):
+    """n = 1024, d = 8, the 33 thetas of `bench.py --train-n 1024 --feat-d 8 --restarts 32`."""
+    _, x, y, lo, hi, thetas, _ = _bench_workload(1024, 8, 32, dtype)
+    assert thetas.shape == (33, 10) and x.dtype == A
+    tol = TOL[A]
+    with _ctx(A) as ctx:
+        ctx.set_data(x, y)
+        lml, grad, status = ctx.lml_grad_batch(thetas, lo=lo, hi=hi)
+        worst = {"lml": 0.0, "grad": 0.0}
+        for b in range(len(thetas)):
+            ref = oracle_lml(thetas[b], x, y, A=A)
+            assert ref is not None and status[b] == 0
+            worst["lml"] = max(worst["lml"], abs(lml[b] - ref.lml) / abs(ref.lml))
+            g_ref = np.array(ref.lml_gradient)
+            worst["grad"] = max(worst["grad"], float(np.abs(grad[b] - g_ref).max() / np.abs(g_ref).max()))
+            assert abs(lml[b] - ref.lml) <= tol * abs(ref.lml), (b, lml[b], ref.lml)
+            np.testing.assert_allclose(grad[b], g_ref, rtol=tol, atol=tol * np.abs(g_ref).max())
+        # mean / variance of 1,000 candidates: GPU model vs the oracle's own alpha and K^-1
+        theta = thetas[0]
+        ref = oracle_lml(theta, x, y, A=A)
+        xs = np.random.default_rng(5).random((1000, 8)).astype(A)
+        model = ctx.model(theta)
+        mean, var = model.predict(xs)
+        model.close()
+    var_ref = np.zeros(1000, dtype=A)
+    mean_ref = ogpr.predict(oracle_kernel(theta), ref.alpha, xs, x, ref.factorization.invc(), var_ref, A)
+    c = math.exp(theta[1])
+    worst["mean"] = float(np.abs(mean - mean_ref).max() / np.abs(mean_ref).max())
+    worst["var"] = float(np.abs(var - var_ref).max() / (c + 1e-5))
+    _note(f"r02_parity_c3_{dtype}.json", worst)
+    np.testing.assert_allclose(mean, mean_ref, rtol=0, atol=tol * np.abs(mean_ref).max())
+    np.testing.assert_allclose(var, var_ref, rtol=0, atol=tol * (c + 1e-5))
+
+
+# ------------------------------------------------------------------------------------------------ (b)
+@pytest.mark.parametrize("A,dtype", [(np.float64, "f64"), (np.float32, "f32")])
+def test_north_star_shape_against_the_oracle(A, dtype):
+    """n = 4096, d = 16: theta 0 of the bench batch against the reference-faithful oracle (one evaluation: ~10 s)."""
+    _, x, y, lo, hi, thetas, _ = _bench_workload(4096, 16, 64, dtype)
+    theta = thetas[0]
+    tol = TOL[A]
+    with _ctx(A) as ctx:
+        ctx.set_data(x, y)
+        lml, grad, status = ctx.lml_grad_batch(theta[None], lo=lo, hi=hi)
+    ref = oracle_lml(theta, x, y, A=A)
+    assert ref is not None and status[0] == 0
+    g_ref = np.array(ref.lml_gradient)
+    _note(f"r02_parity_ns_{dtype}.json", {"lml_gpu": float(lml[0]), "lml_oracle": float(ref.lml),
+                                          "lml_rel": abs(lml[0] - ref.lml) / abs(ref.lml),
+                                          "grad_rel_to_max": float(np.abs(grad[0] - g_ref).max() / np.abs(g_ref).max())})
+    assert abs(lml[0] - ref.lml) <= tol * abs(ref.lml), (lml[0], ref.lml)
+    np.testing.assert_allclose(grad[0], g_ref, rtol=tol, atol=tol * np.abs(g_ref).max())
+
+
+# ------------------------------------------------------------------------------------------------ (c)
+def test_c4_million_candidates_against_the_oracles_own_model():
+    """n = 4096, d = 16, m = 2^20.  alpha and K^-1 come from the ORACLE's factorisation, the
+    prediction from the GPU's own; compared on sampled rows including every chunk edge."""
+    n, d, m = 4096, 16, 1 << 20
+    x, y = synth(n, d)
+    theta = np.array([math.log(0.1), 0.0] + [math.log(0.5)] * d)
+    xs = np.random.default_rng(2).random((m, d))
+    with _ctx(np.float64) as ctx:
+        ctx.set_data(x, y)
+        model = ctx.model(theta, want_alpha=False)
+        mean, var = model.predict(xs)
+        model.close()
+    kern = oracle_kernel(theta)
+    k = kern.kernel(x, x) + 0.1 * np.eye(n)
+    fac = ogpr.factorizec(k, np.float64)
+    alpha = fac.solvec(y)
+    kinv = fac.invc()
+    edges = [0, 1, 63, 64, 127, 128, m - 1, m - 2, m - 64, m - 65]
+    for cb in range(32768, m, 32768):  # the variance GEMM works in chunks of <= 32768 rows
+        edges += [cb - 1, cb, cb + 1]
+    pick = np.unique(np.concatenate([np.array(edges), np.random.default_rng(9).integers(0, m, 1200)]))
+    assert len(pick) >= 1000
+    var_ref = np.zeros(len(pick))
+    mean_ref = ogpr.predict(kern, alpha, xs[pick], x, kinv, var_ref)
+    _note("r02_parity_c4.json", {"rows": int(len(pick)), "mean_abs": float(np.abs(mean[pick] - mean_ref).max()),
+                                 "mean_scale": float(np.abs(mean_ref).max()), "var_abs": float(np.abs(var[pick] - var_ref).max())})
+    np.testing.assert_allclose(mean[pick], mean_ref, rtol=0, atol=1e-9 * np.abs(mean_ref).max())
+    np.testing.assert_allclose(var[pick], var_ref, rtol=0, atol=1e-9 * (1.0 + 1e-5))
+    assert np.isfinite(mean).all() and (var >= 0).all() and (var <= 1.0 + 1e-5 + 1e-12).all()
+
+
+# ------------------------------------------------------------------------------------------------ (d)
+def _oracle_kernel_blocked(kern, x, block=512):
+    """kern.kernel(x, x) evaluated by row blocks on a thread pool (same oracle arithmetic per entry; NumPy's
+    element-wise passes are single-threaded and release the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    n = x.shape[0]
+    out = np.empty((n, n), dtype=x.dtype)
+
+    def work(i0):
+        out[i0:i0 + block] = kern.kernel(x[i0:i0 + block], x)
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        list(ex.map(work, range(0, n, block)))
+    return out
+
+
+def test_c5_shape_against_a_lean_host_evaluation():
+    """n = 16384, d = 32.  Host side: K assembled with the oracle's kernel, LAPACK potrf / potrs / trtri; the LML
+    follows lml.rs:57-59; the noise and amplitude components of the gradient follow from alpha, tr K^-1 and K
+    (g_noise = noise/2 (a.a - tr K^-1), g_c = 1/2 (a.Kc a - n + noise tr K^-1), lml.rs:61-71 with G = noise I and
+    G = Kc); alpha and sampled columns of K^-1 are compared directly."""
+    n, d = 16384, 32
+    x, y = synth(n, d)
+    noise, c = 0.05, 1.2
+    theta = np.array([math.log(noise), math.log(c)] + [math.log(1.5 + 0.02 * k) for k in range(d)])
+    cols = np.array([0, 1, 63, 64, 4095, 8191, 8192, 12345, n - 1])
+    with _ctx(np.float64) as ctx:
+        ctx.set_data(x, y)
+        lml, grad, status = ctx.lml_grad_batch(theta[None])
+        model = ctx.model(theta, want_alpha=True, want_kinv=True)
+        alpha_gpu = model.alpha.copy()
+        kinv_cols_gpu = model.k_inv[:, cols].copy()
+        tr_gpu = float(np.trace(model.k_inv))
+        model.k_inv = None
+        model.close()
+    assert status[0] == 0
+    kc = _oracle_kernel_blocked(oracle_kernel(theta), x)  # 2.1 GB
+    ya_kc = None
+    k = kc.copy()
+    k[np.diag_indices(n)] += noise
+    L, info = lapack.dpotrf(k, lower=1, overwrite_a=1, clean=1)
+    assert info == 0
+    del k
+    alpha, info = lapack.dpotrs(L, y, lower=1)
+    assert info == 0
+    ya_kc = float(alpha @ (kc @ alpha))
+    del kc
+    lml_ref = -0.5 * float(y @ alpha) - float(np.log(np.diag(L)).sum()) - n / 2 * math.log(2 * math.pi)
+    e = np.zeros((n, len(cols)))
+    e[cols, np.arange(len(cols))] = 1.0
+    kinv_cols, info = lapack.dpotrs(L, e, lower=1)
+    assert info == 0
+    Linv, info = lapack.dtrtri(L, lower=1, overwrite_c=1)
+    assert info == 0
+    tr_kinv = float(np.einsum("ij,ij->", Linv, Linv))
+    del Linv, L
+    g_noise = 0.5 * noise * (float(alpha @ alpha) - tr_kinv)
+    g_c = 0.5 * (ya_kc - (n - noise * tr_kinv))
+    _note("r02_parity_c5.json", {"lml_gpu": float(lml[0]), "lml_host": lml_ref, "lml_rel": abs(lml[0] - lml_ref) / abs(lml_ref),
+                                 "g_noise": [float(grad[0, 0]), g_noise], "g_c": [float(grad[0, 1]), g_c],
+                                 "alpha_rel": float(np.abs(alpha_gpu - alpha).max() / np.abs(alpha).max()),
+                                 "kinv_cols_rel": float(np.abs(kinv_cols_gpu - kinv_cols).max() / np.abs(kinv_cols).max()),
+                                 "tr_kinv": [tr_gpu, tr_kinv]})
+    assert abs(lml[0] - lml_ref) <= 1e-9 * abs(lml_ref), (lml[0], lml_ref)
+    gscale = float(np.abs(grad[0]).max())
+    assert abs(grad[0, 0] - g_noise) <= 1e-8 * gscale, (grad[0, 0], g_noise)
+    assert abs(grad[0, 1] - g_c) <= 1e-8 * gscale, (grad[0, 1], g_c)
+    np.testing.assert_allclose(alpha_gpu, alpha, rtol=0, atol=1e-9 * np.abs(alpha).max())
+    np.testing.assert_allclose(kinv_cols_gpu, kinv_cols, rtol=0, atol=1e-9 * np.abs(kinv_cols).max())
+    assert abs(tr_gpu - tr_kinv) <= 1e-9 * tr_kinv
+
+
+# ------------------------------------------------------------------------------------------------ (f)
+def test_f32_north_star_optimum_is_the_precisions_own():
+    """Fits the north-star problem in f64 and in f32 on the GPU (65 runs each), then evaluates the ORACLE in f32
+    and f64 at both fitted thetas.  The CUDA f32 path must agree with the f32 oracle (status and LML to 1e-4) at both
+    points; which optimum f32 prefers is then a property of single precision (the reference warns about its "numeric
+    stability problems" under --use-32, src/bin/hbetune/main.rs:74), not of the CUDA path."""
+    import hbetune_rs_b200 as h
+    n, d, restarts = 4096, 16, 64
+    out = {}
+    fitted = {}
+    for A, dtype in ((np.float64, "f64"), (np.float32, "f32")):
+        _, x, y, lo, hi, _, _ = _bench_workload(n, d, restarts, dtype)
+        bv = h.BoundedValue
+        kernel = h.Product(h.ConstantKernel(bv(math.sqrt(lo[1] * hi[1]), lo[1], hi[1])), h.Matern(2.5, [bv(1.0, 1e-3, 1e3)] * d))
+        with _ctx(A) as ctx:
+            fk = h.FittedKernel.new(ctx, kernel, x, y, h.RNG.new_with_seed(1), restarts, bv(1.0, 1e-2, 1e1))
+            theta = np.array([math.log(fk.noise.value)] + fk.kernel.theta())
+            fitted[dtype] = theta
+            out[f"fit_{dtype}"] = {"lml": fk.lml, "noise": fk.noise.value, "amplitude": fk.kernel.k1.constant.value,
+                                   "n_evals": int(fk.n_evals), "theta": theta.tolist()}
+            fk.model.close()
+    pts = np.array([fitted["f64"], fitted["f32"]])
+    gpu = {}
+    for A, dtype in ((np.float64, "f64"), (np.float32, "f32")):
+        x, y = synth(n, d, A=A)
+        with _ctx(A) as ctx:
+            ctx.set_data(x, y)
+            gpu[dtype] = ctx.lml_grad_batch(pts)
+    x32, y32 = synth(n, d, A=np.float32)
+    x64, y64 = synth(n, d)
+    for i, where in enumerate(("at_f64_optimum", "at_f32_optimum")):
+        o32 = oracle_lml(pts[i], x32, y32, A=np.float32)
+        o64 = oracle_lml(pts[i], x64, y64, A=np.float64)
+        rec = {"oracle_f32": None if o32 is None else float(o32.lml), "oracle_f64": None if o64 is None else float(o64.lml),
+               "cuda_f32": float(gpu["f32"][0][i]), "cuda_f32_status": int(gpu["f32"][2][i]),
+               "cuda_f64": float(gpu["f64"][0][i]), "cuda_f64_status": int(gpu["f64"][2][i])}
+        out[where] = rec
+    _note("r02_f32_optimum.json", out)
+    for where in ("at_f64_optimum", "at_f32_optimum"):
+        rec = out[where]
+        assert (rec["oracle_f32"] is None) == (rec["cuda_f32_status"] != 0), rec
+        assert rec["oracle_f64"] is not None and rec["cuda_f64_status"] == 0
+        assert abs(rec["cuda_f64"] - rec["oracle_f64"]) <= 1e-9 * abs(rec["oracle_f64"]), rec
+        if rec["oracle_f32"] is not None:
+            assert abs(rec["cuda_f32"] - rec["oracle_f32"]) <= 1e-4 * abs(rec["oracle_f32"]), rec
+    # each precision's fit must not be beaten, in its own arithmetic, by the other precision's optimum by more than
+    # the precision's own resolution of the LML
+    assert out["at_f64_optimum"]["cuda_f64"] >= out["at_f32_optimum"]["cuda_f64"] - 1e-6 * abs(out["at_f64_optimum"]["cuda_f64"])

@@ -228,3 +228,63 @@ def test_workspace_limit_chunks_the_batch_bit_identically():
         with pytest.raises(h.HbegpError) as e:
             ctx.lml_grad_batch(thetas[:1])
         assert e.value.code == -3
+
+
+def test_predict_lists_the_variances_below_the_warning_level(capfd):
+    """predict.rs:39-46 prints the offending pre-clamp values; the ABI returns their count and the values
+    (hbegp_predict_warn_values).  A huge amplitude makes c + 1e-5 - |W k*|^2 cancel catastrophically at the training
+    points, so some values fall below -sqrt(1e-5) in any arithmetic."""
+    n, d = 120, 2
+    x, y = synth(n, d)
+    theta = np.array([math.log(1e-2), math.log(1e10), math.log(2.0), math.log(2.0)])
+    xs = np.concatenate([x[:60], np.random.default_rng(1).random((140, d))])
+    with _ctx(np.float64) as ctx:
+        ctx.set_data(x, y)
+        model = ctx.model(theta)
+        mean, var = model.predict(xs, warn=True)
+        count = model.n_below_warn
+        vals, rows = model.warn_values(cap=4096)
+        few, _ = model.warn_values(cap=3)
+        mean2, var2 = model.predict(xs[:5] + 0.25, warn=False)  # a clean call resets the list
+        vals2, _ = model.warn_values()
+        count2 = model.n_below_warn
+        model.close()
+    assert count > 0, "expected cancellation below the warning level at c = 1e10"
+    assert len(vals) == count and (vals < -math.sqrt(1e-5)).all()
+    assert (np.diff(rows) > 0).all() and (var[rows] == 0).all() and (var >= 0).all()
+    np.testing.assert_array_equal(few, vals[:3])
+    err = capfd.readouterr().err
+    assert "Variances below 0 were predicted and will be corrected: " + f"{vals[0]:.2e}" in err
+    assert count2 == len(vals2)
+
+
+def test_large_gemm_tile_reads_no_stale_workspace(monkeypatch):
+    """with the 128-wide GEMM tile the triangular k ranges cover the upper 64x64 block of every
+    128-wide diagonal tile of W = L^-1, which no kernel used to write.  Poison the workspaces with NaNs between two
+    evaluations: the second one must reproduce the first bit for bit and match the oracle."""
+    import hbetune_rs_b200 as h
+    x, y = synth(384, 3)
+    thetas = random_thetas(3, 3, seed=21)
+    res = {}
+    for tile in ("128", "64"):
+        monkeypatch.setenv("HBEGP_TILE", tile)
+        with h.Context(0, h.F64) as ctx:
+            ctx.set_data(x, y)
+            first = ctx.lml_grad_batch(thetas)
+            ctx.debug_poison()
+            second = ctx.lml_grad_batch(thetas)
+            model = ctx.model(thetas[0])
+            ctx.debug_poison()
+            mean, var = model.predict(x[:70] + 0.01)
+            model.close()
+        np.testing.assert_array_equal(first[0], second[0])
+        np.testing.assert_array_equal(first[1], second[1])
+        assert (second[2] == 0).all() and np.isfinite(mean).all() and np.isfinite(var).all()
+        res[tile] = second
+    monkeypatch.delenv("HBEGP_TILE")
+    for b in range(3):
+        ref = oracle_lml(thetas[b], x, y)
+        for tile in res:
+            assert abs(res[tile][0][b] - ref.lml) <= 1e-9 * abs(ref.lml)
+            g_ref = np.array(ref.lml_gradient)
+            np.testing.assert_allclose(res[tile][1][b], g_ref, rtol=1e-8, atol=1e-9 * np.abs(g_ref).max())
