@@ -51,6 +51,11 @@ PROTOTYPES = {
                                          C.c_int, C.c_int, ALLREDUCE_FN, C.c_void_p, C.POINTER(RunResult), C.c_void_p]),
     "hbegp_fit_runs_with": (C.c_int, [BATCH_OBJECTIVE_FN, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int, C.c_int, ALLREDUCE_FN, C.c_void_p, C.POINTER(RunResult), C.c_void_p]),
+    "hbegp_batcher_create": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "hbegp_batcher_eval": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_int)]),
+    "hbegp_batcher_leave": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "hbegp_batcher_results": (C.c_int, [C.c_void_p, C.POINTER(RunResult), C.c_void_p, C.POINTER(C.c_longlong)]),
+    "hbegp_batcher_destroy": (C.c_int, [C.c_void_p]),
     "hbegp_pick_best_run": (C.c_int, [C.c_int, C.POINTER(RunResult)]),
     "hbegp_model_create": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_void_p, C.c_void_p]),

