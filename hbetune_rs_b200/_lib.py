@@ -56,6 +56,27 @@ PROTOTYPES = {
     "hbegp_batcher_leave": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "hbegp_batcher_results": (C.c_int, [C.c_void_p, C.POINTER(RunResult), C.c_void_p, C.POINTER(C.c_longlong)]),
     "hbegp_batcher_destroy": (C.c_int, [C.c_void_p]),
+    "hbegp_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "hbegp_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "hbegp_comm_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_longlong)]),
+    "hbegp_lml_grad_batch_sharded": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hbegp_predict_sharded": (C.c_int, [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_long)]),
+    "hbegp_multi_create": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "hbegp_multi_destroy": (C.c_int, [C.c_void_p]),
+    "hbegp_multi_n_gpus": (C.c_int, [C.c_void_p]),
+    "hbegp_multi_ctx": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "hbegp_multi_set_data": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p]),
+    "hbegp_multi_lml_grad_batch": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hbegp_multi_fit_runs": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.POINTER(RunResult), C.c_void_p]),
+    "hbegp_multi_model_create": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_void_p, C.c_void_p]),
+    "hbegp_multi_model_destroy": (C.c_int, [C.c_void_p]),
+    "hbegp_multi_model_replica": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "hbegp_multi_predict": (C.c_int, [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_long)]),
     "hbegp_pick_best_run": (C.c_int, [C.c_int, C.POINTER(RunResult)]),
     "hbegp_model_create": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_void_p, C.c_void_p]),

@@ -446,5 +446,34 @@ inline cudaError_t launch(const GemmArgs<float>& a, int batch, cudaStream_t stre
     return cudaGetLastError();
 }
 
+// Policy (process-wide, set by hbegp_ctx_create from HBEGP_TF32 / HBEGP_TF32_MIN): whether f32 contractions go through
+// the tensor path, and the smallest min(M, N) for which they do (below it one 128 x 128 tile per CTA leaves the GPU
+// emptier than the 64 x 64 FFMA tiles and the per-CTA pipeline start-up dominates).
+inline bool& enabled() {
+    static bool on = true;
+    return on;
+}
+inline int& min_extent() {
+    static int v = 256;
+    return v;
+}
+
 }  // namespace tf32
+
+// Dispatch used by the engine: f64 -> DMMA kernel; f32 -> tcgen05 3xTF32 when the policy allows and the operands meet
+// the 128-wide-tile invariant (`aligned128`: every 128-wide diagonal block of a triangular operand has exact zeros
+// above its diagonal), else the FFMA kernel.
+template <typename T, bool AK, bool BKM>
+inline cudaError_t launch_gemm_auto(const GemmArgs<T>& a, int batch, cudaStream_t stream, bool aligned128) {
+    if constexpr (std::is_same<T, float>::value) {
+        if (tf32::enabled() && aligned128 && (a.M < a.N ? a.M : a.N) >= tf32::min_extent()) return tf32::launch<AK, BKM>(a, batch, stream);
+    }
+    return launch_gemm<T, AK, BKM>(a, batch, stream);
+}
+
+template <typename T>
+inline bool gemm_uses_tf32(int M, int N, bool aligned128) {
+    return std::is_same<T, float>::value && tf32::enabled() && aligned128 && (M < N ? M : N) >= tf32::min_extent();
+}
+
 }  // namespace hbegp

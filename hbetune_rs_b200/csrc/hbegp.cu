@@ -20,14 +20,17 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
 #include "../../include/hbegp.h"
 #include "gemm.cuh"
+#include "gemm_tf32.cuh"
 #include "kernels.cuh"
 #include "lbfgs.h"
 #include "adapter.h"
+#include "comm.h"
 
 namespace hbegp {
 
@@ -164,7 +167,48 @@ struct EngineBase {
     virtual int kernel_matrix(double nu, int d, const double* theta, long n1, const void* x1, long n2, const void* x2, void* out) = 0;
     virtual int kernel_theta_grad(double nu, int d, const double* theta, long n, const void* x, void* k_out, void* grad_out) = 0;
     double next_model_noise = 0.0;  // clamped noise of the model being built (fit.rs:164; see Model::noise_clamped)
+
+    // ---- exchange between GPUs (multi-process mode: one context per rank, hbegp_comm_init) -- NCCL on device buffers
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    DevBuf comm_send, comm_recv;
+    void* h_comm = nullptr;  // pinned
+    size_t h_comm_bytes = 0;
+    cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;
+    double coll_ms_total = 0.0;
+    long long n_collectives = 0;
+    int last_eval_cnt = -1;  // evaluations whose results the device buffers below hold (-1: spread over several chunks)
+    virtual const double* dev_lml() const = 0;
+    virtual const double* dev_grad() const = 0;
+    virtual const int* dev_status() const = 0;
+    virtual Model* new_empty_model(int nu2, const std::vector<double>& prm_h, double noise_clamped) = 0;
+    virtual int alloc_data(long n, int d) = 0;  // set_data without the copies (the receiving side of a broadcast)
+    virtual void* dev_x() = 0;
+    virtual void* dev_y() = 0;
+    virtual size_t elem_size() const = 0;
+    int ensure_host_comm(size_t bytes) {
+        if (bytes <= h_comm_bytes) return HBEGP_OK;
+        if (h_comm) cudaFreeHost(h_comm);
+        h_comm = nullptr;
+        h_comm_bytes = 0;
+        CUDA_TRY(cudaMallocHost(&h_comm, bytes));
+        h_comm_bytes = bytes;
+        return HBEGP_OK;
+    }
+    void note_collective() {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev_c0, ev_c1) == cudaSuccess) coll_ms_total += ms;
+        n_collectives++;
+    }
 };
+
+#define NCCL_TRY(expr)                                                                                        \
+    do {                                                                                                      \
+        ncclResult_t _r = (expr);                                                                             \
+        if (_r != ncclSuccess)                                                                                \
+            return fail(HBEGP_ERR_CUDA, std::string(#expr) + ": " + Nccl::get().GetErrorString(_r) + " (" + __FILE__ + ":" + \
+                                            std::to_string(__LINE__) + ")");                                  \
+    } while (0)
 
 struct Model {
     EngineBase* eng = nullptr;
@@ -179,6 +223,7 @@ struct Model {
     // prm_h[0] is the unclamped value the fit evaluated (fit.rs:96 does not clamp); they differ only when the optimum
     // sits outside the noise bounds by rounding.
     double noise_clamped = 0.0;
+    bool w_aligned128 = false;  // W meets the 128-wide-tile invariant (Engine::aligned128)
     // values < -sqrt(1e-5) of the last host prediction (predict.rs:39-46 lists them), in row order
     DevBuf warn_rows, warn_vals;
     std::vector<double> last_warn_vals;
@@ -196,6 +241,7 @@ struct Model {
     }
     virtual int predict_device(long m, const void* xs, void* mean, void* var, long* n_below_device) = 0;
     virtual int predict_host(long m, const void* xs, void* mean, void* var, long* n_below) = 0;
+    virtual int predict_sharded(long m, const void* xs, void* mean, void* var, long* n_below) = 0;
     virtual int predict_acquisition(int mode, const hbegp_ynorm* yn, long m, const void* xs, double param, void* out1,
                                     void* out2, long* best, long* n_below) = 0;
     DevBuf acq1, acq2, argv, argi;
@@ -255,13 +301,27 @@ struct Engine : EngineBase {
         if (h_status) cudaFreeHost(h_status);
     }
 
+    void* dev_x() override { return dX.p; }
+    void* dev_y() override { return dY.p; }
+    size_t elem_size() const override { return sizeof(T); }
+    int alloc_data(long n_, int d_) override { return set_data(n_, d_, nullptr, nullptr, true); }
+    const double* dev_lml() const override { return (const double*)d_lml.p; }
+    const double* dev_grad() const override { return (const double*)d_grad.p; }
+    const int* dev_status() const override { return (const int*)d_status.p; }
+    Model* new_empty_model(int nu2, const std::vector<double>& prm_h, double noise_clamped) override;
+
     int p() const { return d + 2; }
+    // The recursion puts its 128-multiple blocks first (chol_inv) and k_node128 zeroes the (0,1) block of every bottom
+    // node, so with the fused node enabled every 128-wide diagonal tile of W has exact zeros above its diagonal -- the
+    // invariant the 128-wide GEMM tiles (f64 HBEGP_TILE=128, f32 tcgen05) need for their triangular k ranges.
+    bool aligned128() const { return use_node128; }
     long mstride() const { return (long)np * np; }
     int ntiles_lower() const { int t = np / TILE; return t * (t + 1) / 2; }
     int nchunks() const { return (np + 255) / 256; }
 
     int set_data(long n_, int d_, const void* x, const void* y, bool on_device) override {
-        if (n_ <= 0 || d_ <= 0 || !x || !y) return fail(HBEGP_ERR_INVALID, "set_data: n, d must be positive and x, y non-null");
+        const bool alloc_only = on_device && !x && !y;  // alloc_data(): buffers sized and padded, contents arrive by broadcast
+        if (n_ <= 0 || d_ <= 0 || (!alloc_only && (!x || !y))) return fail(HBEGP_ERR_INVALID, "set_data: n, d must be positive and x, y non-null");
         if (n_ > 46000) return fail(HBEGP_ERR_INVALID, "set_data: n too large for a single-GPU factorisation");
         if ((2 * (size_t)d_ * TILE + 2 * TILE) * sizeof(T) + 8 * (size_t)(d_ + 2) * sizeof(double) > kMaxFeatureSmem)
             return fail(HBEGP_ERR_UNSUPPORTED, "set_data: too many features for the shared-memory tiles of the assembly kernels");
@@ -280,6 +340,7 @@ struct Engine : EngineBase {
         }
         cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
         CUDA_TRY(cudaMemsetAsync(dY.p, 0, (size_t)np * sizeof(T), stream));
+        if (alloc_only) return HBEGP_OK;
         CUDA_TRY(cudaMemcpyAsync(dX.p, x, (size_t)n * d * sizeof(T), kind, stream));
         CUDA_TRY(cudaMemcpyAsync(dY.p, y, (size_t)n * sizeof(T), kind, stream));
         if (!on_device) CUDA_TRY(cudaStreamSynchronize(stream));  // the caller may free x / y
@@ -405,7 +466,7 @@ struct Engine : EngineBase {
         // 1. panel solve as a product with the inverse: L21 = A21 W11^T  -> W(2,1)
         g.A = A21; g.B = W11; g.C = W21; g.M = s2; g.N = s1; g.K = s1; g.kmode = K_LE_N; g.lower_only = 0;
         g.alpha = T(1); g.beta = T(0);
-        CUDA_TRY((launch_gemm<T, true, true>(g, cnt, st))); launches++;
+        CUDA_TRY((launch_gemm_auto<T, true, true>(g, cnt, st, aligned128()))); launches++;
         // 3. T = L21 W11 -> A(2,1); independent of step 2 and of the second half, so it may run on the side stream
         cudaStream_t st3 = st;
         if (sd.st) {
@@ -415,19 +476,19 @@ struct Engine : EngineBase {
         }
         g.A = W21; g.B = W11; g.C = A21; g.M = s2; g.N = s1; g.K = s1; g.kmode = K_GE_N; g.lower_only = 0;
         g.alpha = T(1); g.beta = T(0);
-        CUDA_TRY((launch_gemm<T, true, false>(g, cnt, st3))); launches++;
+        CUDA_TRY((launch_gemm_auto<T, true, false>(g, cnt, st3, aligned128()))); launches++;
         if (sd.st) CUDA_TRY(cudaEventRecord(sd.b, sd.st));
         // 2. trailing update: A22 -= L21 L21^T (lower tiles)
         g.A = W21; g.B = W21; g.C = A22; g.M = s2; g.N = s2; g.K = s1; g.kmode = K_FULL; g.lower_only = 1;
         g.alpha = T(-1); g.beta = T(1);
-        CUDA_TRY((launch_gemm<T, true, true>(g, cnt, st))); launches++;
+        CUDA_TRY((launch_gemm_auto<T, true, true>(g, cnt, st, aligned128()))); launches++;
         if ((rc = chol_inv(st, s0, cnt, r0 + s1, s2, sd))) return rc;
         // (a nested node may have re-recorded sd.b later on the side stream: waiting for that implies our product)
         if (sd.st) CUDA_TRY(cudaStreamWaitEvent(st, sd.b, 0));
         // 4. W21 = -W22 T
         g.A = W22; g.B = A21; g.C = W21; g.M = s2; g.N = s1; g.K = s2; g.kmode = K_LE_M; g.lower_only = 0;
         g.alpha = T(-1); g.beta = T(0);
-        CUDA_TRY((launch_gemm<T, true, false>(g, cnt, st))); launches++;
+        CUDA_TRY((launch_gemm_auto<T, true, false>(g, cnt, st, aligned128()))); launches++;
         return HBEGP_OK;
     }
 
@@ -439,7 +500,7 @@ struct Engine : EngineBase {
         g.A = Wb; g.B = Wb; g.C = Ab; g.M = np; g.N = np; g.K = np; g.kmode = K_GE_M; g.lower_only = 1;
         g.alpha = T(1); g.beta = T(0);
         g.rowsumsq = nullptr;
-        CUDA_TRY((launch_gemm<T, false, false>(g, cnt, st))); launches++;
+        CUDA_TRY((launch_gemm_auto<T, false, false>(g, cnt, st, aligned128()))); launches++;
         return HBEGP_OK;
     }
 
@@ -599,6 +660,7 @@ struct Engine : EngineBase {
         if (B == 0) return HBEGP_OK;
         CUDA_TRY(cudaSetDevice(device));
         if ((rc = ensure_capacity((use_graphs && pad_batches && np <= 2048 && B > 4) ? (B + 3) / 4 * 4 : B))) return rc;
+        last_eval_cnt = (B <= cap) ? B : -1;
         for (int b0 = 0; b0 < B; b0 += cap) {
             int cnt = std::min(cap, B - b0);
             for (int b = 0; b < cnt; b++) fill_params(theta + (size_t)(b0 + b) * p(), lo, hi, h_prm + (size_t)b * p());
@@ -845,17 +907,16 @@ struct ModelT : Model {
         if (m <= 64 && (size_t)m * d * sizeof(T) <= 40 * 1024) return predict_small<NU2>((int)m, xs, mean, var, nb);
         const size_t ksm = (2 * (size_t)d * TILE + TILE) * sizeof(T);
         const int ttiles = np / TILE;
-        // split the train tiles over grid.y when the candidate tiles alone would leave most SMs idle
-        auto col_split = [&](int row_tiles) {
-            int s = (3 * 148 + row_tiles - 1) / row_tiles;
-            return std::max(1, std::min(s, ttiles));
-        };
+        // The train tiles are split over grid.y in FIXED groups of 16 (1024 training rows); the partial means are summed
+        // in group order by k_var_finish.  A fixed group size (instead of one chosen from the number of candidate
+        // tiles) makes a candidate's mean independent of how many rows are predicted with it -- the same bits whether
+        // the rows arrive in one call, in chunks, or sharded over GPUs -- and keeps the GPU full for few candidates.
+        const int tpc = 16, ns = (ttiles + tpc - 1) / tpc;
         int rc;
         if (var == nullptr) {
             const int chunk_cap = 1 << 20;
             for (long row0 = 0; row0 < m; row0 += chunk_cap) {
                 const int rows = round_up(std::min<long>(chunk_cap, m - row0), TILE);
-                const int S = col_split(rows / TILE), tpc = (ttiles + S - 1) / S, ns = (ttiles + tpc - 1) / tpc;
                 T* pm = nullptr;
                 if (ns > 1) {
                     if ((rc = pmean.ensure((size_t)ns * rows * sizeof(T)))) return rc;
@@ -874,13 +935,13 @@ struct ModelT : Model {
             return HBEGP_OK;
         }
         const int chunk = (int)std::min<long>(predict_chunk_rows(), round_up(m, 128));
-        const int bn = pick_gemm_tile<T>(128, np);  // rows are always a multiple of 128
-        const int ntile = np / bn;
+        const bool tf = gemm_uses_tf32<T>(128, np, w_aligned128);  // rows are always a multiple of 128
+        const int bn = tf ? 128 : pick_gemm_tile<T>(128, np);
+        const int ntile = (np + bn - 1) / bn;
         if ((rc = kstar.ensure((size_t)chunk * np * sizeof(T)))) return rc;
         if ((rc = part.ensure((size_t)chunk * ntile * sizeof(T)))) return rc;
         for (long row0 = 0; row0 < m; row0 += chunk) {
             const int rows = (int)std::min<long>(chunk, round_up(m - row0, 128));
-            const int S = col_split(rows / TILE), tpc = (ttiles + S - 1) / S, ns = (ttiles + tpc - 1) / tpc;
             T* pm = nullptr;
             if (ns > 1) {
                 if ((rc = pmean.ensure((size_t)ns * rows * sizeof(T)))) return rc;
@@ -899,7 +960,7 @@ struct ModelT : Model {
             g.rowsumsq = (T*)part.p; g.ld_rs = ntile; g.s_rs = 0;
             // keep ~48 MB of k* rows resident in L2 while W streams (ncu before: 35 GB of DRAM reads per 1 GB chunk)
             g.raster_group = (int)std::max<size_t>(1, ((size_t)48 << 20) / ((size_t)bn * np * sizeof(T)));
-            CUDA_TRY((launch_gemm<T, true, true>(g, 1, st)));
+            CUDA_TRY((launch_gemm_auto<T, true, true>(g, 1, st, w_aligned128)));
             e->launches++;
             k_var_finish<T><<<(rows + 255) / 256, 256, 0, st>>>((const T*)part.p, ntile, ntile, rows, m, row0, (T)c, var, nb, pm, ns, rows, mean,
                                                                 (long*)warn_rows.p, (T*)warn_vals.p, kWarnCap);
@@ -949,6 +1010,58 @@ struct ModelT : Model {
         CUDA_TRY(cudaStreamSynchronize(e->stream));
         if (n_below) *n_below = (long)hb;
         return fetch_warn_list((long)hb);
+    }
+
+    // Candidate rows in contiguous blocks over the ranks of the context's communicator: every rank passes the same m
+    // rows, predicts its block into the send buffer (mean | variance), one ncclAllGather of the device buffers plus a
+    // sum all-reduce of the below-warning count, one copy back.
+    int predict_sharded(long m, const void* xs, void* mean, void* var, long* n_below) override {
+        Engine<T>* e = static_cast<Engine<T>*>(eng);
+        if (!e->comm || e->comm_world == 1) return predict_host(m, xs, mean, var, n_below);
+        if (m < 0 || (m > 0 && (!xs || !mean))) return fail(HBEGP_ERR_INVALID, "predict_sharded: bad arguments");
+        if (n_below) *n_below = 0;
+        if (m == 0) return HBEGP_OK;
+        Nccl& nc = Nccl::get();
+        const int world = e->comm_world, rank = e->comm_rank;
+        const long blk = (m + world - 1) / world;
+        const long lo = std::min(m, rank * blk), hi = std::min(m, lo + blk), mine = hi - lo;
+        const int cols = var ? 2 : 1;
+        const size_t blk_bytes = (size_t)cols * blk * sizeof(T);
+        CUDA_TRY(cudaSetDevice(e->device));
+        int rc;
+        if ((rc = e->comm_send.ensure(blk_bytes))) return rc;
+        if ((rc = e->comm_recv.ensure(blk_bytes * world))) return rc;
+        if ((rc = e->ensure_host_comm(blk_bytes * world))) return rc;
+        if ((rc = nbelow.ensure(sizeof(unsigned long long)))) return rc;
+        if ((rc = xs_tmp.ensure((size_t)std::max<long>(mine, 1) * d * sizeof(T)))) return rc;
+        T* send = (T*)e->comm_send.p;
+        CUDA_TRY(cudaMemsetAsync(send, 0, blk_bytes, e->stream));
+        CUDA_TRY(cudaMemsetAsync(nbelow.p, 0, sizeof(unsigned long long), e->stream));
+        if (mine > 0) {
+            CUDA_TRY(cudaMemcpyAsync(xs_tmp.p, (const T*)xs + (size_t)lo * d, (size_t)mine * d * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+            if ((rc = predict_device(mine, xs_tmp.p, send, var ? send + blk : nullptr, nullptr))) return rc;
+        }
+        CUDA_TRY(cudaEventRecord(e->ev_c0, e->stream));
+        NCCL_TRY(nc.GroupStart());
+        NCCL_TRY(nc.AllGather(send, e->comm_recv.p, blk_bytes, ncclChar, e->comm, e->stream));
+        NCCL_TRY(nc.AllReduce(nbelow.p, nbelow.p, 1, ncclUint64, ncclSum, e->comm, e->stream));
+        NCCL_TRY(nc.GroupEnd());
+        CUDA_TRY(cudaEventRecord(e->ev_c1, e->stream));
+        unsigned long long hb = 0;
+        CUDA_TRY(cudaMemcpyAsync(e->h_comm, e->comm_recv.p, blk_bytes * world, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaMemcpyAsync(&hb, nbelow.p, sizeof(hb), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        e->note_collective();
+        for (int r = 0; r < world; r++) {
+            const long r0 = std::min(m, r * blk), cnt = std::min(m, r0 + blk) - r0;
+            const T* src = (const T*)((const char*)e->h_comm + (size_t)r * blk_bytes);
+            if (cnt > 0) std::memcpy((T*)mean + r0, src, (size_t)cnt * sizeof(T));
+            if (cnt > 0 && var) std::memcpy((T*)var + r0, src + blk, (size_t)cnt * sizeof(T));
+        }
+        if (n_below) *n_below = (long)hb;
+        last_warn_vals.clear();  // the value list is per rank; only the count is exchanged
+        last_warn_rows.clear();
+        return HBEGP_OK;
     }
 
     // The (row, value) pairs below the warning level of the prediction that just finished, sorted by row
@@ -1069,6 +1182,7 @@ int Engine<T>::finish_model(int nu2, Model** out, double* lml, void* alpha_out, 
     m->c = (double)h_prm[1];
     m->prm_h.assign(h_prm, h_prm + p());
     m->noise_clamped = next_model_noise;
+    m->w_aligned128 = aligned128();
     auto bail = [&](int code) { delete m; return code; };
     if ((rc = m->W.ensure((size_t)np * np * sizeof(T)))) return bail(rc);
     if ((rc = m->alpha.ensure((size_t)np * sizeof(T)))) return bail(rc);
@@ -1101,6 +1215,32 @@ int Engine<T>::finish_model(int nu2, Model** out, double* lml, void* alpha_out, 
     models.push_back(m);
     *out = m;
     return HBEGP_OK;
+}
+
+// A model object with its device buffers allocated but not filled: the receiving side of a model broadcast
+// (hbegp_multi_model_create: one GPU evaluates, the others receive W, alpha, X^T / l over NVLink).
+template <typename T>
+Model* Engine<T>::new_empty_model(int nu2, const std::vector<double>& prm_host, double noise_clamped) {
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    ModelT<T>* m = new ModelT<T>();
+    m->eng = this;
+    m->use_pool(&model_pool);
+    m->dtype = dtype;
+    m->n = n;
+    m->d = d;
+    m->np = np;
+    m->nu2 = nu2;
+    m->c = prm_host[1];
+    m->prm_h = prm_host;
+    m->noise_clamped = noise_clamped;
+    m->w_aligned128 = aligned128();
+    if (m->W.ensure((size_t)np * np * sizeof(T)) || m->alpha.ensure((size_t)np * sizeof(T)) || m->xsT.ensure((size_t)d * np * sizeof(T)) ||
+        m->ls.ensure((size_t)d * sizeof(T)) || m->ldp.ensure((size_t)(np / TILE) * sizeof(T))) {
+        delete m;
+        return nullptr;
+    }
+    models.push_back(m);
+    return m;
 }
 
 // Append path of `extend`.  The prior model's W11 = L11^-1 over its first r1 rows stays valid
@@ -1166,7 +1306,9 @@ int Engine<T>::model_extend(Model* prior_, Model** out, double* lml, void* alpha
     const int nu2 = prior->nu2;
     const bool want_kinv = kinv_out != nullptr;
     // the append needs at least one complete 64-row leaf of the prior model and the old rows as a prefix
-    int r1 = (int)(std::min<long>(prior->n, n) / TILE) * TILE;
+    // (a multiple of 128 rows of the prior are kept so that the appended blocks stay aligned with the 128-wide tiles)
+    int r1 = (int)(std::min<long>(prior->n, n) / (2 * TILE)) * (2 * TILE);
+    if (!prior->w_aligned128) r1 = 0;
     if (prior->n > n || !same_noise) r1 = 0;
     if (r1 > 0) {
         CUDA_TRY(cudaMemcpyAsync(prm.p, h_prm, (size_t)p() * sizeof(T), cudaMemcpyHostToDevice, stream));
@@ -1208,6 +1350,11 @@ static int configure_gemms() {
     HBEGP_CFG(64, 64, 32, 32, true, false);
     HBEGP_CFG(64, 64, 32, 32, false, false);
 #undef HBEGP_CFG
+    if (std::is_same<T, float>::value) {
+        CUDA_TRY((tf32::configure<true, true>()));
+        CUDA_TRY((tf32::configure<true, false>()));
+        CUDA_TRY((tf32::configure<false, false>()));
+    }
     // kernels whose dynamic shared memory grows with the feature count d (two d x 64 operand tiles)
     const int big = (int)kMaxFeatureSmem;
     CUDA_TRY(cudaFuncSetAttribute(k_leaf<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem_bytes<T>()));
@@ -1233,13 +1380,17 @@ static int configure_gemms() {
 // different times, and the result is bit-identical to the single-process loop.
 using BatchEval = std::function<int(int, const double*, double*, double*, int*)>;
 
+// exchange(B, Bm, rc, xbuf): shares one round between the ranks.  xbuf arrives host-packed (B records of p + 2 doubles
+// plus a failure flag, zero where this rank has nothing) and must leave as the element-wise sum over all ranks.
+using RoundExchange = std::function<int(int, int, int, std::vector<double>&)>;
+
 static int fit_runs_impl(int p, const BatchEval& eval, int n_runs, const double* starts, const double* blo, const double* bhi,
                          int maxeval, int rank, int world, hbegp_allreduce_fn allreduce, void* ar_user,
-                         hbegp_run_result* results, double* best_theta) {
+                         hbegp_run_result* results, double* best_theta, const RoundExchange* exchange = nullptr) {
     if (n_runs < 0 || (n_runs > 0 && (!starts || !blo || !bhi || !results || !best_theta)))
         return fail(HBEGP_ERR_INVALID, "fit_runs: bad arguments");
-    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !allreduce))
-        return fail(HBEGP_ERR_INVALID, "fit_runs: need 0 <= rank < world and an all-reduce callback when world > 1");
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !allreduce && !exchange))
+        return fail(HBEGP_ERR_INVALID, "fit_runs: need 0 <= rank < world and, when world > 1, an all-reduce callback or hbegp_comm_init");
     std::vector<double> lb(p), ub(p);
     for (int k = 0; k < p; k++) {
         if (!(blo[k] > 0) || !(bhi[k] >= blo[k])) return fail(HBEGP_ERR_INVALID, "fit_runs: bounds must satisfy 0 < lo <= hi");
@@ -1298,7 +1449,12 @@ static int fit_runs_impl(int p, const BatchEval& eval, int n_runs, const double*
                 rec[1] = (double)stm[i];
                 for (int k = 0; k < p; k++) rec[2 + k] = ok ? gradm[(size_t)i * p + k] : 0.0;
             }
-            if (allreduce(ar_user, xbuf.data(), (long)xbuf.size())) return fail(HBEGP_ERR_INVALID, "fit_runs: the all-reduce callback failed");
+            if (exchange) {
+                int xrc = (*exchange)(B, Bm, rc, xbuf);
+                if (xrc) return xrc;
+            } else if (allreduce(ar_user, xbuf.data(), (long)xbuf.size())) {
+                return fail(HBEGP_ERR_INVALID, "fit_runs: the all-reduce callback failed");
+            }
             if (rc) return rc;
             if (xbuf[(size_t)B * w] != 0.0) return fail(HBEGP_ERR_CUDA, "fit_runs: the evaluation failed on another rank");
             for (int b = 0; b < B; b++) {
@@ -1326,6 +1482,41 @@ static int fit_runs_impl(int p, const BatchEval& eval, int n_runs, const double*
             if (opt[r].done()) R.final_f = opt[r].f();
         }
     }
+    return HBEGP_OK;
+}
+
+// ------------------------------------------------------------------------------------ exchange between GPUs (NCCL)
+// One round of the balanced restart loop: this rank's records are packed ON THE DEVICE from the evaluation's result
+// buffers into the zero-filled round record (positions rank, rank + world, ... like the dealing in fit_runs_impl), one
+// ncclAllReduce(sum) over NVLink shares the round -- every element is summed with zeros only, so all ranks see
+// bit-identical values -- and one device-to-host copy brings it back.
+static int nccl_exchange_round(EngineBase* e, int B, int Bm, int rc_eval, std::vector<double>& xbuf) {
+    Nccl& nc = Nccl::get();
+    const int p = e->d + 2, w = p + 2;
+    const size_t count = (size_t)B * w + 1;
+    CUDA_TRY(cudaSetDevice(e->device));
+    int rc;
+    if ((rc = e->comm_send.ensure(count * sizeof(double)))) return rc;
+    if ((rc = e->ensure_host_comm(count * sizeof(double)))) return rc;
+    double* d_round = (double*)e->comm_send.p;
+    if (rc_eval == HBEGP_OK && Bm > 0 && e->last_eval_cnt == Bm) {
+        CUDA_TRY(cudaMemsetAsync(d_round, 0, count * sizeof(double), e->stream));
+        k_pack_round<<<Bm, 64, 0, e->stream>>>(e->dev_lml(), e->dev_grad(), e->dev_status(), Bm, p, e->comm_rank, e->comm_world, d_round);
+        e->launches++;
+        CUDA_TRY(cudaGetLastError());
+    } else {
+        // nothing evaluated here this round, a failed evaluation (flag only), or results spread over several chunks:
+        // the host-packed record goes up as it is
+        std::memcpy(e->h_comm, xbuf.data(), count * sizeof(double));
+        CUDA_TRY(cudaMemcpyAsync(d_round, e->h_comm, count * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    }
+    CUDA_TRY(cudaEventRecord(e->ev_c0, e->stream));
+    NCCL_TRY(nc.AllReduce(d_round, d_round, count, ncclDouble, ncclSum, e->comm, e->stream));
+    CUDA_TRY(cudaEventRecord(e->ev_c1, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(e->h_comm, d_round, count * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->note_collective();
+    std::memcpy(xbuf.data(), e->h_comm, count * sizeof(double));
     return HBEGP_OK;
 }
 
@@ -1477,6 +1668,16 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
         gemm_tile_pref() = (s64 && atoi(s64) == 128) ? 128 : 64;
         gemm_tile_pref_f32() = (s32 && atoi(s32) == 128) ? 128 : 64;
     }
+    {
+        const char* t = getenv("HBEGP_TF32");
+        const char* tm = getenv("HBEGP_TF32_MIN");
+        tf32::enabled() = !(t && atoi(t) == 0);
+        tf32::min_extent() = tm ? std::max(64, atoi(tm)) : 256;
+        if (dtype == HBEGP_F32 && tf32::enabled() && !tf32::encode_fn()) {
+            delete e;
+            return fail(HBEGP_ERR_CUDA, "ctx_create: cuTensorMapEncodeTiled is not available from this driver (set HBEGP_TF32=0)");
+        }
+    }
     bool graphs_on = true;
     if (const char* s = getenv("HBEGP_GRAPHS")) graphs_on = atoi(s) != 0;
     if (dtype == HBEGP_F64) { static_cast<Engine<double>*>(e)->streams_forced = forced; static_cast<Engine<double>*>(e)->use_graphs = graphs_on; }
@@ -1542,6 +1743,12 @@ int hbegp_ctx_destroy(hbegp_ctx* ctx) {
     if (e->main_a) cudaEventDestroy(e->main_a);
     if (e->main_b) cudaEventDestroy(e->main_b);
     if (e->fork_ev) cudaEventDestroy(e->fork_ev);
+    if (e->comm) Nccl::get().CommDestroy(e->comm);
+    e->comm_send.release();
+    e->comm_recv.release();
+    if (e->h_comm) cudaFreeHost(e->h_comm);
+    if (e->ev_c0) cudaEventDestroy(e->ev_c0);
+    if (e->ev_c1) cudaEventDestroy(e->ev_c1);
     if (e->own_stream) cudaStreamDestroy(e->stream);
     delete e;
     delete ctx;
@@ -1585,8 +1792,133 @@ int hbegp_fit_runs_sharded(hbegp_ctx* ctx, double nu, int n_runs, const double* 
     BatchEval eval = [&](int B, const double* th, double* lml, double* grad, int* st) {
         return e->eval_batch(nu, B, th, bounds_lo, bounds_hi, lml, grad, st);
     };
+    if (world > 1 && !allreduce) {
+        if (!e->comm || e->comm_world != world || e->comm_rank != rank)
+            return fail(HBEGP_ERR_INVALID, "fit_runs_sharded: no all-reduce callback and no matching communicator (hbegp_comm_init)");
+        RoundExchange ex = [e](int B, int Bm, int rc, std::vector<double>& xbuf) { return nccl_exchange_round(e, B, Bm, rc, xbuf); };
+        return fit_runs_impl(e->d + 2, eval, n_runs, starts, bounds_lo, bounds_hi, maxeval, rank, world, nullptr, nullptr, results,
+                             best_theta, &ex);
+    }
     return fit_runs_impl(e->d + 2, eval, n_runs, starts, bounds_lo, bounds_hi, maxeval, rank, world, allreduce, allreduce_user,
                          results, best_theta);
+}
+
+// ---- communicator (multi-process mode: one context per rank)
+int hbegp_comm_unique_id(void* id_out) {
+    if (!id_out) return fail(HBEGP_ERR_INVALID, "comm_unique_id: null output");
+    Nccl& nc = Nccl::get();
+    if (!nc.ok()) return fail(HBEGP_ERR_CUDA, nc.error);
+    ncclUniqueId id;
+    NCCL_TRY(nc.GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == HBEGP_COMM_ID_BYTES, "ncclUniqueId size");
+    std::memcpy(id_out, &id, sizeof(id));
+    return HBEGP_OK;
+}
+
+static int comm_attach(EngineBase* e, ncclComm_t comm, int rank, int world) {
+    e->comm = comm;
+    e->comm_rank = rank;
+    e->comm_world = world;
+    if (!e->ev_c0) {
+        CUDA_TRY(cudaEventCreate(&e->ev_c0));
+        CUDA_TRY(cudaEventCreate(&e->ev_c1));
+    }
+    return HBEGP_OK;
+}
+
+int hbegp_comm_init(hbegp_ctx* ctx, int world, int rank, const void* id) {
+    if (!ctx || !id || world < 1 || rank < 0 || rank >= world) return fail(HBEGP_ERR_INVALID, "comm_init: bad arguments");
+    EngineBase* e = ctx->eng;
+    if (e->comm) return fail(HBEGP_ERR_INVALID, "comm_init: this context already has a communicator");
+    Nccl& nc = Nccl::get();
+    if (!nc.ok()) return fail(HBEGP_ERR_CUDA, nc.error);
+    CUDA_TRY(cudaSetDevice(e->device));
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, sizeof(uid));
+    ncclComm_t comm = nullptr;
+    NCCL_TRY(nc.CommInitRank(&comm, world, uid, rank));
+    return comm_attach(e, comm, rank, world);
+}
+
+int hbegp_comm_info(hbegp_ctx* ctx, int* rank, int* world, int* nccl_version, double* collective_ms, long long* n_collectives) {
+    if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");
+    EngineBase* e = ctx->eng;
+    if (rank) *rank = e->comm_rank;
+    if (world) *world = e->comm ? e->comm_world : 1;
+    if (nccl_version) {
+        *nccl_version = 0;
+        if (Nccl::get().ok()) Nccl::get().GetVersion(nccl_version);
+    }
+    if (collective_ms) *collective_ms = e->coll_ms_total;
+    if (n_collectives) *n_collectives = e->n_collectives;
+    return HBEGP_OK;
+}
+
+// B thetas known to every rank; rank r evaluates thetas r, r + world, ...; one ncclAllGather of the per-rank record
+// blocks (device buffers) and one device-to-host copy give every rank all B results.
+int hbegp_lml_grad_batch_sharded(hbegp_ctx* ctx, double nu, int B, const double* theta, const double* lo, const double* hi,
+                                 double* lml, double* grad, int* status) {
+    if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");
+    EngineBase* e = ctx->eng;
+    if (!e->comm || e->comm_world == 1) return e->eval_batch(nu, B, theta, lo, hi, lml, grad, status);
+    if (B < 0 || (B > 0 && (!theta || !lml))) return fail(HBEGP_ERR_INVALID, "lml_grad_batch_sharded: bad arguments");
+    if (B == 0) return HBEGP_OK;
+    Nccl& nc = Nccl::get();
+    const int p = e->d + 2, w = p + 2, world = e->comm_world, rank = e->comm_rank;
+    const int blk = (B + world - 1) / world;          // records per rank (zero padded)
+    const size_t blk_count = (size_t)blk * w + 1;     // + this rank's failure flag
+    std::vector<double> th, l, g;
+    std::vector<int> st;
+    int Bm = 0;
+    for (int b = rank; b < B; b += world) Bm++;
+    th.resize((size_t)Bm * p);
+    l.resize(Bm);
+    g.resize((size_t)Bm * p);
+    st.resize(Bm);
+    for (int i = 0; i < Bm; i++) std::memcpy(&th[(size_t)i * p], theta + (size_t)(rank + i * world) * p, sizeof(double) * p);
+    int rc_eval = Bm ? e->eval_batch(nu, Bm, th.data(), lo, hi, l.data(), g.data(), st.data()) : HBEGP_OK;
+    const std::string eval_err = rc_eval ? g_last_error : std::string();
+    CUDA_TRY(cudaSetDevice(e->device));
+    int rc;
+    if ((rc = e->comm_send.ensure(blk_count * sizeof(double)))) return rc;
+    if ((rc = e->comm_recv.ensure(blk_count * world * sizeof(double)))) return rc;
+    if ((rc = e->ensure_host_comm(blk_count * world * sizeof(double)))) return rc;
+    double* d_send = (double*)e->comm_send.p;
+    CUDA_TRY(cudaMemsetAsync(d_send, 0, blk_count * sizeof(double), e->stream));
+    if (rc_eval == HBEGP_OK && Bm > 0 && e->last_eval_cnt == Bm) {
+        k_pack_round<<<Bm, 64, 0, e->stream>>>(e->dev_lml(), e->dev_grad(), e->dev_status(), Bm, p, 0, 1, d_send);
+        e->launches++;
+        CUDA_TRY(cudaGetLastError());
+    } else {
+        double* hs = (double*)e->h_comm;
+        std::memset(hs, 0, blk_count * sizeof(double));
+        for (int i = 0; i < Bm && !rc_eval; i++) {
+            const bool ok = st[i] == HBEGP_OK;
+            hs[(size_t)i * w] = ok ? l[i] : 0.0;
+            hs[(size_t)i * w + 1] = ok ? 0.0 : 1.0;
+            for (int k = 0; k < p; k++) hs[(size_t)i * w + 2 + k] = ok ? g[(size_t)i * p + k] : 0.0;
+        }
+        hs[(size_t)blk * w] = rc_eval ? 1.0 : 0.0;
+        CUDA_TRY(cudaMemcpyAsync(d_send, hs, blk_count * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    }
+    CUDA_TRY(cudaEventRecord(e->ev_c0, e->stream));
+    NCCL_TRY(nc.AllGather(d_send, e->comm_recv.p, blk_count, ncclDouble, e->comm, e->stream));
+    CUDA_TRY(cudaEventRecord(e->ev_c1, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(e->h_comm, e->comm_recv.p, blk_count * world * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->note_collective();
+    if (rc_eval) return fail(rc_eval, eval_err);
+    const double* all = (const double*)e->h_comm;
+    for (int r = 0; r < world; r++)
+        if (all[(size_t)r * blk_count + (size_t)blk * w] != 0.0) return fail(HBEGP_ERR_CUDA, "lml_grad_batch_sharded: the evaluation failed on another rank");
+    for (int b = 0; b < B; b++) {
+        const double* rec = all + (size_t)(b % world) * blk_count + (size_t)(b / world) * w;
+        const bool bad = rec[1] != 0.0;
+        lml[b] = bad ? -std::numeric_limits<double>::infinity() : rec[0];
+        if (status) status[b] = bad ? HBEGP_NOT_PD : HBEGP_OK;
+        if (grad) std::memcpy(grad + (size_t)b * p, rec + 2, sizeof(double) * p);
+    }
+    return HBEGP_OK;
 }
 
 int hbegp_fit_runs_with(hbegp_batch_objective_fn objective, void* objective_user, int p, int n_runs, const double* starts,
@@ -1787,6 +2119,12 @@ int hbegp_predict(hbegp_model* model, long m, const void* xs, void* mean, void* 
     return model->m->predict_host(m, xs, mean, var, n_below_warn);
 }
 
+int hbegp_predict_sharded(hbegp_model* model, long m, const void* xs, void* mean, void* var, long* n_below_warn) {
+    if (!model || !model->m) return fail(HBEGP_ERR_INVALID, "null model");
+    if (!model->m->eng) return fail(HBEGP_ERR_INVALID, "the model's context has been destroyed");
+    return model->m->predict_sharded(m, xs, mean, var, n_below_warn);
+}
+
 int hbegp_predict_device(hbegp_model* model, long m, const void* xs_device, void* mean_device, void* var_device,
                          long* n_below_warn_device) {
     if (!model) return fail(HBEGP_ERR_INVALID, "null model");
@@ -1898,6 +2236,258 @@ int hbegp_debug_factor(hbegp_ctx* ctx, double nu, const double* theta, void* k, 
     if (!ctx || !theta) return fail(HBEGP_ERR_INVALID, "debug_factor: bad arguments");
     if (ctx->eng->n <= 0) return fail(HBEGP_ERR_INVALID, "no training data: call hbegp_set_data first");
     return ctx->eng->debug_factor(nu, theta, k, w, kinv, status);
+}
+
+}  // extern "C"
+
+// =================================================================================== single-process multi-GPU
+// The reference is ONE process (src/bin/hbetune/main.rs:255-355), so a drop-in estimator needs a handle that spans the
+// GPUs of the box without any help from the host language: hbegp_multi owns one context per device and their NCCL
+// communicators.  Work is split only where the path shards: the thetas of a batched evaluation / the live
+// runs of a fit round are dealt round-robin to the GPUs and evaluated concurrently (one host thread per GPU; the
+// results come back to the one process, so no collective is needed there), candidate rows of a prediction go out in
+// contiguous blocks.  What does travel between GPUs travels over NVLink with NCCL on device buffers: the training data
+// (ncclBroadcast at set_data) and the fitted model (W = L^-1, alpha, X^T / l: one evaluation on GPU 0, broadcast to the
+// replicas -- 134 MB at n = 4096, cheaper than n^3 flops per replica).
+struct hbegp_multi {
+    std::vector<hbegp_ctx*> ctx;
+    std::vector<ncclComm_t> comms;
+    int dtype = HBEGP_F64;
+};
+struct hbegp_multi_model {
+    hbegp_multi* mm = nullptr;
+    std::vector<hbegp_model*> models;
+};
+
+template <typename F>
+static int on_all_gpus(int n, F&& f) {  // f(i) -> status, one host thread per GPU; first failure wins
+    std::vector<int> rc(n, HBEGP_OK);
+    std::vector<std::string> err(n);
+    std::vector<std::thread> th;
+    for (int i = 1; i < n; i++)
+        th.emplace_back([&, i] {
+            rc[i] = f(i);
+            if (rc[i]) err[i] = g_last_error;
+        });
+    rc[0] = f(0);
+    if (rc[0]) err[0] = g_last_error;
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n; i++)
+        if (rc[i]) return fail(rc[i], "GPU " + std::to_string(i) + ": " + err[i]);
+    return HBEGP_OK;
+}
+
+extern "C" {
+
+int hbegp_multi_create(int n_gpus, const int* devices, int dtype, hbegp_multi** out) {
+    if (!out || n_gpus < 1) return fail(HBEGP_ERR_INVALID, "multi_create: bad arguments");
+    *out = nullptr;
+    hbegp_multi* mm = new hbegp_multi();
+    mm->dtype = dtype;
+    std::vector<int> devs(n_gpus);
+    for (int i = 0; i < n_gpus; i++) devs[i] = devices ? devices[i] : i;
+    for (int i = 0; i < n_gpus; i++) {
+        hbegp_ctx* c = nullptr;
+        int rc = hbegp_ctx_create(devs[i], dtype, nullptr, &c);
+        if (rc) {
+            hbegp_multi_destroy(mm);
+            return rc;
+        }
+        mm->ctx.push_back(c);
+    }
+    if (n_gpus > 1) {
+        Nccl& nc = Nccl::get();
+        if (!nc.ok()) {
+            hbegp_multi_destroy(mm);
+            return fail(HBEGP_ERR_CUDA, nc.error);
+        }
+        mm->comms.assign(n_gpus, nullptr);
+        ncclResult_t r = nc.CommInitAll(mm->comms.data(), n_gpus, devs.data());
+        if (r != ncclSuccess) {
+            mm->comms.clear();
+            hbegp_multi_destroy(mm);
+            return fail(HBEGP_ERR_CUDA, std::string("ncclCommInitAll: ") + nc.GetErrorString(r));
+        }
+        for (int i = 0; i < n_gpus; i++) {
+            int rc = comm_attach(mm->ctx[i]->eng, mm->comms[i], i, n_gpus);  // the context owns (and destroys) its communicator
+            if (rc) {
+                hbegp_multi_destroy(mm);
+                return rc;
+            }
+        }
+    }
+    *out = mm;
+    return HBEGP_OK;
+}
+
+int hbegp_multi_destroy(hbegp_multi* mm) {
+    if (!mm) return HBEGP_OK;
+    for (hbegp_ctx* c : mm->ctx) hbegp_ctx_destroy(c);
+    delete mm;
+    return HBEGP_OK;
+}
+
+int hbegp_multi_n_gpus(const hbegp_multi* mm) { return mm ? (int)mm->ctx.size() : 0; }
+hbegp_ctx* hbegp_multi_ctx(hbegp_multi* mm, int i) { return (mm && i >= 0 && i < (int)mm->ctx.size()) ? mm->ctx[i] : nullptr; }
+
+// Group-broadcast `bytes` from GPU 0's buffer to every replica's (NCCL over NVLink), then wait for all streams.
+static int multi_broadcast(hbegp_multi* mm, const std::vector<void*>& bufs, size_t bytes) {
+    const int G = (int)mm->ctx.size();
+    if (G == 1 || bytes == 0) return HBEGP_OK;
+    Nccl& nc = Nccl::get();
+    EngineBase* e0 = mm->ctx[0]->eng;
+    CUDA_TRY(cudaSetDevice(e0->device));
+    CUDA_TRY(cudaEventRecord(e0->ev_c0, e0->stream));
+    NCCL_TRY(nc.GroupStart());
+    for (int i = 0; i < G; i++) {
+        EngineBase* e = mm->ctx[i]->eng;
+        NCCL_TRY(nc.Broadcast(bufs[0], bufs[i], bytes, ncclChar, 0, e->comm, e->stream));
+    }
+    NCCL_TRY(nc.GroupEnd());
+    CUDA_TRY(cudaSetDevice(e0->device));
+    CUDA_TRY(cudaEventRecord(e0->ev_c1, e0->stream));
+    for (int i = 0; i < G; i++) {
+        EngineBase* e = mm->ctx[i]->eng;
+        CUDA_TRY(cudaSetDevice(e->device));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
+    e0->note_collective();
+    return HBEGP_OK;
+}
+
+int hbegp_multi_set_data(hbegp_multi* mm, long n, int d, const void* x, const void* y) {
+    if (!mm) return fail(HBEGP_ERR_INVALID, "null multi-GPU handle");
+    const int G = (int)mm->ctx.size();
+    int rc = mm->ctx[0]->eng->set_data(n, d, x, y, false);  // one host-to-device copy ...
+    if (rc) return rc;
+    std::vector<void*> bx(G), by(G);
+    for (int i = 0; i < G; i++) {
+        EngineBase* e = mm->ctx[i]->eng;
+        if (i > 0 && (rc = e->alloc_data(n, d))) return rc;
+        bx[i] = e->dev_x();
+        by[i] = e->dev_y();
+    }
+    const size_t es = mm->ctx[0]->eng->elem_size();
+    if ((rc = multi_broadcast(mm, bx, (size_t)n * d * es))) return rc;  // ... then NVLink to the replicas
+    return multi_broadcast(mm, by, (size_t)n * es);
+}
+
+// B thetas dealt round-robin over the GPUs, evaluated concurrently, results gathered by the host threads.
+static int multi_eval(hbegp_multi* mm, double nu, int B, const double* theta, const double* lo, const double* hi, double* lml,
+                      double* grad, int* status) {
+    const int G = (int)mm->ctx.size();
+    if (B <= 0) return HBEGP_OK;
+    const int p = mm->ctx[0]->eng->d + 2;
+    if (G == 1 || B == 1) return mm->ctx[0]->eng->eval_batch(nu, B, theta, lo, hi, lml, grad, status);
+    return on_all_gpus(G, [&](int i) -> int {
+        std::vector<int> mine;
+        for (int b = i; b < B; b += G) mine.push_back(b);
+        const int Bm = (int)mine.size();
+        if (!Bm) return HBEGP_OK;
+        std::vector<double> th((size_t)Bm * p), l(Bm), g(grad ? (size_t)Bm * p : 0);
+        std::vector<int> st(Bm);
+        for (int k = 0; k < Bm; k++) std::memcpy(&th[(size_t)k * p], theta + (size_t)mine[k] * p, sizeof(double) * p);
+        int rc = mm->ctx[i]->eng->eval_batch(nu, Bm, th.data(), lo, hi, l.data(), grad ? g.data() : nullptr, st.data());
+        if (rc) return rc;
+        for (int k = 0; k < Bm; k++) {
+            lml[mine[k]] = l[k];
+            if (status) status[mine[k]] = st[k];
+            if (grad) std::memcpy(grad + (size_t)mine[k] * p, &g[(size_t)k * p], sizeof(double) * p);
+        }
+        return HBEGP_OK;
+    });
+}
+
+int hbegp_multi_lml_grad_batch(hbegp_multi* mm, double nu, int B, const double* theta, const double* lo, const double* hi,
+                               double* lml, double* grad, int* status) {
+    if (!mm) return fail(HBEGP_ERR_INVALID, "null multi-GPU handle");
+    if (B < 0 || (B > 0 && (!theta || !lml))) return fail(HBEGP_ERR_INVALID, "multi_lml_grad_batch: bad arguments");
+    if (mm->ctx[0]->eng->n <= 0) return fail(HBEGP_ERR_INVALID, "no training data: call hbegp_multi_set_data first");
+    return multi_eval(mm, nu, B, theta, lo, hi, lml, grad, status);
+}
+
+int hbegp_multi_fit_runs(hbegp_multi* mm, double nu, int n_runs, const double* starts, const double* bounds_lo,
+                         const double* bounds_hi, int maxeval, hbegp_run_result* results, double* best_theta) {
+    if (!mm) return fail(HBEGP_ERR_INVALID, "null multi-GPU handle");
+    if (mm->ctx[0]->eng->n <= 0) return fail(HBEGP_ERR_INVALID, "no training data: call hbegp_multi_set_data first");
+    BatchEval eval = [&](int B, const double* th, double* lml, double* grad, int* st) {
+        return multi_eval(mm, nu, B, th, bounds_lo, bounds_hi, lml, grad, st);
+    };
+    return fit_runs_impl(mm->ctx[0]->eng->d + 2, eval, n_runs, starts, bounds_lo, bounds_hi, maxeval, 0, 1, nullptr, nullptr, results,
+                         best_theta);
+}
+
+int hbegp_multi_model_create(hbegp_multi* mm, double nu, const double* theta, const double* lo, const double* hi,
+                             hbegp_multi_model** out, double* lml, void* alpha_out, void* kinv_out) {
+    if (!mm || !out) return fail(HBEGP_ERR_INVALID, "multi_model_create: bad arguments");
+    *out = nullptr;
+    const int G = (int)mm->ctx.size();
+    hbegp_model* m0 = nullptr;
+    int rc = hbegp_model_create(mm->ctx[0], nu, theta, lo, hi, &m0, lml, alpha_out, kinv_out);
+    if (rc) return rc;
+    hbegp_multi_model* h = new hbegp_multi_model();
+    h->mm = mm;
+    h->models.push_back(m0);
+    Model* src = m0->m;
+    for (int i = 1; i < G; i++) {
+        Model* r = mm->ctx[i]->eng->new_empty_model(src->nu2, src->prm_h, src->noise_clamped);
+        if (!r) {
+            hbegp_multi_model_destroy(h);
+            return fail(HBEGP_ERR_NOMEM, "multi_model_create: could not allocate the replica on GPU " + std::to_string(i));
+        }
+        h->models.push_back(new hbegp_model{r});
+    }
+    struct Part {
+        DevBuf Model::*buf;
+        size_t bytes;
+    };
+    const size_t es = mm->ctx[0]->eng->elem_size(), np = (size_t)src->np;
+    const Part parts[] = {{&Model::W, np * np * es}, {&Model::alpha, np * es}, {&Model::xsT, (size_t)src->d * np * es},
+                          {&Model::ls, (size_t)src->d * es}, {&Model::ldp, (np / TILE) * es}};
+    for (const Part& part : parts) {
+        std::vector<void*> bufs(G);
+        for (int i = 0; i < G; i++) bufs[i] = (h->models[i]->m->*(part.buf)).p;
+        if ((rc = multi_broadcast(mm, bufs, part.bytes))) {
+            hbegp_multi_model_destroy(h);
+            return rc;
+        }
+    }
+    *out = h;
+    return HBEGP_OK;
+}
+
+int hbegp_multi_model_destroy(hbegp_multi_model* h) {
+    if (!h) return HBEGP_OK;
+    for (hbegp_model* m : h->models) hbegp_model_destroy(m);
+    delete h;
+    return HBEGP_OK;
+}
+
+hbegp_model* hbegp_multi_model_replica(hbegp_multi_model* h, int i) {
+    return (h && i >= 0 && i < (int)h->models.size()) ? h->models[i] : nullptr;
+}
+
+int hbegp_multi_predict(hbegp_multi_model* h, long m, const void* xs, void* mean, void* var, long* n_below_warn) {
+    if (!h) return fail(HBEGP_ERR_INVALID, "null multi-GPU model");
+    if (m < 0 || (m > 0 && (!xs || !mean))) return fail(HBEGP_ERR_INVALID, "multi_predict: bad arguments");
+    if (n_below_warn) *n_below_warn = 0;
+    if (m == 0) return HBEGP_OK;
+    const int G = (int)h->models.size();
+    if (G == 1 || m < 256) return hbegp_predict(h->models[0], m, xs, mean, var, n_below_warn);
+    const size_t es = h->mm->ctx[0]->eng->elem_size();
+    const int d = h->models[0]->m->d;
+    const long blk = (m + G - 1) / G;
+    std::vector<long> below(G, 0);
+    int rc = on_all_gpus(G, [&](int i) -> int {
+        const long r0 = std::min(m, i * blk), cnt = std::min(m, r0 + blk) - r0;
+        if (cnt <= 0) return HBEGP_OK;
+        return hbegp_predict(h->models[i], cnt, (const char*)xs + (size_t)r0 * d * es, (char*)mean + (size_t)r0 * es,
+                             var ? (char*)var + (size_t)r0 * es : nullptr, &below[i]);
+    });
+    if (rc) return rc;
+    if (n_below_warn)
+        for (long b : below) *n_below_warn += b;
+    return HBEGP_OK;
 }
 
 }  // extern "C"

@@ -1045,6 +1045,25 @@ __global__ void k_kernel_theta_grad(const T* __restrict__ x, int n, int d, const
     }
 }
 
+// One record per evaluation for the exchange between GPUs: [lml, status, grad_0 .. grad_{p-1}] with lml and gradient
+// zeroed and status = 1 when the evaluation failed (like eval_batch reports it to the host), written at record
+// position pos0 + i * pos_stride of `round` (records of p + 2 doubles).
+__global__ void k_pack_round(const double* __restrict__ lml, const double* __restrict__ grad, const int* __restrict__ status,
+                             int cnt, int p, int pos0, int pos_stride, double* __restrict__ round) {
+    const int i = blockIdx.x;
+    if (i >= cnt) return;
+    const double l = lml[i];
+    const bool bad = status[i] != 0 || !(l - l == 0.0);
+    double* rec = round + (long)(pos0 + i * pos_stride) * (p + 2);
+    for (int t = threadIdx.x; t < p + 2; t += blockDim.x) {
+        double v;
+        if (t == 0) v = bad ? 0.0 : l;
+        else if (t == 1) v = bad ? 1.0 : 0.0;
+        else v = bad ? 0.0 : grad[(long)i * p + t - 2];
+        rec[t] = v;
+    }
+}
+
 template <typename T>
 __global__ void k_fill(T* __restrict__ out, long n, T v) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -96,11 +96,58 @@ int hbegp_fit_runs(hbegp_ctx* ctx, double nu, int n_runs, const double* starts, 
  * evaluates its share and `allreduce` (called once per round on every rank) must sum `count` doubles element-wise
  * over all ranks in place -- e.g. ncclAllReduce / torch.distributed.all_reduce(SUM).  All ranks return the records of
  * ALL runs, bit-identical to the single-process loop (each value is summed with zeros only).  The work stays
- * balanced while runs finish at different times (a static split of the runs leaves GPUs idle in the tail). */
+ * balanced while runs finish at different times (a static split of the runs leaves GPUs idle in the tail).
+ * With allreduce = NULL the exchange runs inside the library on the communicator of hbegp_comm_init (ncclAllReduce on
+ * the device-resident round record).  If the exchange fails on one rank that rank returns an error while its peers are
+ * still inside the collective: the caller must tear the job down (NCCL's own failure mode; there is no recovery). */
 typedef int (*hbegp_allreduce_fn)(void* user, double* values, long count); /* 0 on success */
 int hbegp_fit_runs_sharded(hbegp_ctx* ctx, double nu, int n_runs, const double* starts, const double* bounds_lo,
                            const double* bounds_hi, int maxeval, int rank, int world, hbegp_allreduce_fn allreduce,
                            void* allreduce_user, hbegp_run_result* results, double* best_theta);
+
+/* ---- exchange between GPUs inside the library: NCCL over NVLink on device buffers ----------------------------
+ * Multi-process mode (one process and one context per GPU; the launcher only has to hand every rank the same 128-byte
+ * id, e.g. over MPI / torch.distributed / a file): rank 0 calls hbegp_comm_unique_id, every rank hbegp_comm_init.
+ * Afterwards hbegp_fit_runs_sharded may be called with allreduce = NULL (the per-round record is packed on the device
+ * and summed with ncclAllReduce), and the two calls below shard a batched evaluation / a prediction with one
+ * ncclAllGather of the device-resident results and one device-to-host copy.  libnccl.so.2 is loaded at run time (the
+ * copy already in the process if there is one, else $HBEGP_NCCL_LIB, else the system library). */
+#define HBEGP_COMM_ID_BYTES 128
+int hbegp_comm_unique_id(void* id_out /* HBEGP_COMM_ID_BYTES */);
+int hbegp_comm_init(hbegp_ctx* ctx, int world, int rank, const void* id);
+/* Any output may be NULL.  collective_ms / n_collectives: device time (CUDA events around the NCCL calls) and count of
+ * the collectives this context has issued so far. */
+int hbegp_comm_info(hbegp_ctx* ctx, int* rank, int* world, int* nccl_version, double* collective_ms, long long* n_collectives);
+/* hbegp_lml_grad_batch over the ranks of the communicator: every rank passes the same B thetas and receives all B
+ * results; rank r evaluates thetas r, r + world, ...  (src/util/gradmin.rs:19-30: the restarts are independent). */
+int hbegp_lml_grad_batch_sharded(hbegp_ctx* ctx, double nu, int B, const double* theta, const double* lo, const double* hi,
+                                 double* lml, double* grad, int* status);
+/* hbegp_predict over the ranks of the model's context: every rank passes the same m candidate rows and receives all m
+ * means / variances; rank r predicts the r-th contiguous block of ceil(m / world) rows.  (The list of
+ * hbegp_predict_warn_values is not exchanged, only the count.) */
+int hbegp_predict_sharded(hbegp_model* model, long m, const void* xs, void* mean, void* var, long* n_below_warn);
+
+/* Single-process mode -- what a drop-in for the reference needs, which is one process (src/bin/hbetune/main.rs:255-355):
+ * one handle over n_gpus devices (devices = NULL: 0 .. n_gpus - 1).  Thetas of a batch / live runs of a fit round are
+ * dealt round-robin to the GPUs and evaluated concurrently; candidate rows go out in contiguous blocks; training data
+ * and the fitted model are replicated with ncclBroadcast.  Results are bit-identical to one GPU. */
+typedef struct hbegp_multi hbegp_multi;
+typedef struct hbegp_multi_model hbegp_multi_model;
+int hbegp_multi_create(int n_gpus, const int* devices, int dtype, hbegp_multi** out);
+int hbegp_multi_destroy(hbegp_multi* multi);
+int hbegp_multi_n_gpus(const hbegp_multi* multi);
+hbegp_ctx* hbegp_multi_ctx(hbegp_multi* multi, int i); /* the context of GPU i (owned by the handle) */
+int hbegp_multi_set_data(hbegp_multi* multi, long n, int d, const void* x, const void* y);
+int hbegp_multi_lml_grad_batch(hbegp_multi* multi, double nu, int B, const double* theta, const double* lo, const double* hi,
+                               double* lml, double* grad, int* status);
+int hbegp_multi_fit_runs(hbegp_multi* multi, double nu, int n_runs, const double* starts, const double* bounds_lo,
+                         const double* bounds_hi, int maxeval, hbegp_run_result* results, double* best_theta);
+/* One evaluation on GPU 0 (as hbegp_model_create), then the model travels to the other GPUs over NVLink. */
+int hbegp_multi_model_create(hbegp_multi* multi, double nu, const double* theta, const double* lo, const double* hi,
+                             hbegp_multi_model** out, double* lml, void* alpha_out, void* kinv_out);
+int hbegp_multi_model_destroy(hbegp_multi_model* model);
+hbegp_model* hbegp_multi_model_replica(hbegp_multi_model* model, int i); /* GPU i's replica (owned by the multi model) */
+int hbegp_multi_predict(hbegp_multi_model* model, long m, const void* xs, void* mean, void* var, long* n_below_warn);
 
 /* The loop over a caller-supplied batched objective instead of the GPU (the restart loop of gradmin.rs:7-33 for any
  * function): objective(user, B, p, theta[B*p], lml[B], grad[B*p], status[B]) returns 0 on success; status[b] != 0
@@ -151,7 +198,8 @@ int hbegp_model_create(hbegp_ctx* ctx, double nu, const double* theta, const dou
  * in-tree call site appends the validation samples to the evaluation history, minimize.rs:629-644 -- only the
  * added rows are factorised (an O(n^2 k) block append, checked on the device; the result is the same model up to
  * rounding); otherwise this is the full evaluation.  *appended (may be NULL) reports which: 1 append, 0 full.
- * The prior stays valid and must belong to `ctx`. */
+  * The append keeps the first floor(n_prior / 128) * 128 rows of the prior factor (at least 128), so that appended blocks stay aligned with
+ * the 128-wide GEMM tiles.  The prior stays valid and must belong to `ctx`. */
 int hbegp_model_extend(hbegp_ctx* ctx, hbegp_model* prior, hbegp_model** out, double* lml, void* alpha_out,
                        void* kinv_out, int* appended);
 int hbegp_model_destroy(hbegp_model* model);
