@@ -8,7 +8,7 @@ sharding over ``torch.distributed``).
 """
 from ._lib import F32, F64, NOT_PD, OK, HbegpError, lib  # noqa: F401
 from .gpr import (BoundedValue, BoundsError, ConstantKernel, Context, FittedKernel, Matern, Model,  # noqa: F401
-                  Product, predict)
+                  MultiContext, MultiModel, Product, predict)
 
 from .estimator import (LINEAR, LOGARITHMIC, EstimatorGPR, SummaryStatistics, SurrogateModelGPR, YNormalize,  # noqa: F401
                         estimate_amplitude, expected_improvement, find_best_candidate_by_ei,

@@ -40,6 +40,9 @@ PROTOTYPES = {
     "hbegp_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "hbegp_ctx_destroy": (C.c_int, [C.c_void_p]),
     "hbegp_ctx_set_workspace_limit": (C.c_int, [C.c_void_p, C.c_ulonglong]),
+    "hbegp_ctx_set_resident_models": (C.c_int, [C.c_void_p, C.c_int]),
+    "hbegp_ctx_model_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong),
+                                        C.POINTER(C.c_longlong)]),
     "hbegp_ctx_launch_count": (C.c_longlong, [C.c_void_p]),
     "hbegp_set_data": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p]),
     "hbegp_set_data_device": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p]),

@@ -152,7 +152,10 @@ struct EngineBase {
     int d = 0, np = 0;
     size_t ws_limit = 0;
     long long launches = 0;
-    std::vector<Model*> models;  // live models of this context (orphaned, not leaked, on ctx_destroy)
+    std::vector<Model*> models;  // live models of this context, oldest first (orphaned, not leaked, on ctx_destroy)
+    int resident_limit = 4;      // models that keep their factor on the device (<= 0: all); hbegp_ctx_set_resident_models
+    long long n_evictions = 0, n_rebuilds = 0;
+    void evict_old_models();
     BufPool model_pool;          // buffers of destroyed models (see BufPool)
     virtual ~EngineBase() {}
     virtual int set_data(long n, int d, const void* x, const void* y, bool on_device) = 0;
@@ -224,6 +227,17 @@ struct Model {
     // sits outside the noise bounds by rounding.
     double noise_clamped = 0.0;
     bool w_aligned128 = false;  // W meets the 128-wide-tile invariant (Engine::aligned128)
+    // Retained-model policy (the minimizer keeps EVERY generation's model, minimize.rs:331, :407): only
+    // the newest few models of a context keep their n x n factor W = L^-1 on the device.  An older one gives W and its
+    // prediction scratch back to the pool (O(n d) stays: X^T / l, alpha, the parameters) and refactorises on its next
+    // predict_* call.
+    bool evicted = false;
+    void evict() {
+        W.release(); kstar.release(); part.release(); pmean.release(); xs_tmp.release(); mean_tmp.release(); var_tmp.release();
+        acq1.release(); acq2.release();
+        evicted = true;
+    }
+    virtual int ensure_resident() = 0;
     // values < -sqrt(1e-5) of the last host prediction (predict.rs:39-46 lists them), in row order
     DevBuf warn_rows, warn_vals;
     std::vector<double> last_warn_vals;
@@ -251,6 +265,18 @@ struct Model {
             b->pool = pl;
     }
 };
+
+inline void EngineBase::evict_old_models() {
+    if (resident_limit <= 0) return;
+    int resident = 0;
+    for (auto it = models.rbegin(); it != models.rend(); ++it) {
+        if ((*it)->evicted) continue;
+        if (++resident > resident_limit) {
+            (*it)->evict();
+            n_evictions++;
+        }
+    }
+}
 
 static int nu_to_nu2(double nu, int* nu2) {
     const double eps = std::numeric_limits<double>::epsilon();
@@ -935,13 +961,14 @@ struct ModelT : Model {
             return HBEGP_OK;
         }
         const int chunk = (int)std::min<long>(predict_chunk_rows(), round_up(m, 128));
-        const bool tf = gemm_uses_tf32<T>(128, np, w_aligned128);  // rows are always a multiple of 128
-        const int bn = tf ? 128 : pick_gemm_tile<T>(128, np);
-        const int ntile = (np + bn - 1) / bn;
         if ((rc = kstar.ensure((size_t)chunk * np * sizeof(T)))) return rc;
-        if ((rc = part.ensure((size_t)chunk * ntile * sizeof(T)))) return rc;
+        if ((rc = part.ensure((size_t)chunk * (np / TILE) * sizeof(T)))) return rc;  // one partial per 64-wide column tile at most
         for (long row0 = 0; row0 < m; row0 += chunk) {
             const int rows = (int)std::min<long>(chunk, round_up(m - row0, 128));
+            // column-tile width of the variance GEMM: must be the one launch_gemm_auto picks for exactly this shape
+            const bool tf = gemm_uses_tf32<T>(rows, np, w_aligned128);
+            const int bn = tf ? 128 : pick_gemm_tile<T>(128, np);  // rows are always a multiple of 128
+            const int ntile = (np + bn - 1) / bn;
             T* pm = nullptr;
             if (ns > 1) {
                 if ((rc = pmean.ensure((size_t)ns * rows * sizeof(T)))) return rc;
@@ -976,6 +1003,7 @@ struct ModelT : Model {
         Engine<T>* e = static_cast<Engine<T>*>(eng);
         CUDA_TRY(cudaSetDevice(e->device));
         int rc;
+        if (var && (rc = ensure_resident())) return rc;  // the mean needs alpha and X^T / l only
         if ((rc = nbelow.ensure(sizeof(unsigned long long)))) return rc;
         if (var && (rc = warn_rows.ensure(kWarnCap * sizeof(long)))) return rc;
         if (var && (rc = warn_vals.ensure(kWarnCap * sizeof(T)))) return rc;
@@ -988,6 +1016,75 @@ struct ModelT : Model {
 
     int predict_acquisition(int mode, const hbegp_ynorm* yn, long m, const void* xs, double param, void* out1, void* out2,
                             long* best, long* n_below) override;
+
+    // Rebuilds the evicted factor: K from the model's own scaled inputs and parameters, the recursion of the fit, W back
+    // into the model.  The engine's workspaces are used when they are large enough for this model's size, temporary ones
+    // otherwise; the context's current training data is not touched.
+    template <int NU2>
+    int rebuild_nu() {
+        Engine<T>* e = static_cast<Engine<T>*>(eng);
+        const int p = d + 2;
+        const size_t msz = (size_t)np * np * sizeof(T);
+        DevBuf tA, tW, tldp, tprm, tstatus;
+        int rc;
+        const bool fits = e->A.bytes >= msz && e->W.bytes >= msz && e->ldp.bytes >= (size_t)(np / TILE) * sizeof(T) && e->d_status.bytes >= sizeof(int);
+        auto done = [&](int code) {
+            for (DevBuf* b : {&tA, &tW, &tldp, &tprm, &tstatus}) b->release();
+            return code;
+        };
+        if (!fits) {
+            if ((rc = tA.ensure(msz)) || (rc = tW.ensure(msz)) || (rc = tldp.ensure((size_t)(np / TILE) * sizeof(T))) ||
+                (rc = tstatus.ensure(2 * sizeof(int))))
+                return done(rc);
+            std::swap(e->A, tA); std::swap(e->W, tW); std::swap(e->ldp, tldp); std::swap(e->d_status, tstatus);
+        }
+        auto restore = [&] {
+            if (!fits) { std::swap(e->A, tA); std::swap(e->W, tW); std::swap(e->ldp, tldp); std::swap(e->d_status, tstatus); }
+        };
+        if ((rc = tprm.ensure((size_t)p * sizeof(T))) || (rc = W.ensure(msz))) { restore(); return done(rc); }
+        std::vector<T> prm_host(p);
+        for (int k = 0; k < p; k++) prm_host[k] = (T)prm_h[k];
+        cudaStream_t st = e->stream;
+        const long save_n = e->n;
+        const int save_np = e->np, save_d = e->d;
+        e->n = n; e->np = np; e->d = this->d;  // the recursion reads the matrix size from the engine
+        cudaError_t ce = cudaMemcpyAsync(tprm.p, prm_host.data(), (size_t)p * sizeof(T), cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(e->d_status.p, 0, sizeof(int), st);
+        if (ce == cudaSuccess) {
+            const int nt = (np / TILE) * (np / TILE + 1) / 2;
+            k_assemble<T, NU2><<<dim3(nt, 1, 1), 256, 2 * (size_t)this->d * TILE * sizeof(T), st>>>((const T*)xsT.p, (int)n, this->d, np, (const T*)tprm.p, p,
+                                                                                                   (T*)e->A.p, (long)np * np, 0);
+            e->launches++;
+            ce = cudaGetLastError();
+        }
+        rc = HBEGP_OK;
+        if (ce == cudaSuccess) rc = e->chol_inv(st, 0, 1, 0, np);
+        int hs = 1;
+        if (ce == cudaSuccess && rc == HBEGP_OK) ce = cudaMemcpyAsync(W.p, e->W.p, msz, cudaMemcpyDeviceToDevice, st);
+        if (ce == cudaSuccess && rc == HBEGP_OK) ce = cudaMemcpyAsync(&hs, e->d_status.p, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess && rc == HBEGP_OK) ce = cudaStreamSynchronize(st);
+        e->n = save_n; e->np = save_np; e->d = save_d;
+        restore();
+        if (ce != cudaSuccess) return done(fail(HBEGP_ERR_CUDA, std::string("model rebuild: ") + cudaGetErrorString(ce)));
+        if (rc) return done(rc);
+        if (hs) return done(fail(HBEGP_ERR_CUDA, "model rebuild: the kernel matrix of a previously fitted model is not positive definite"));
+        evicted = false;
+        e->n_rebuilds++;
+        return done(HBEGP_OK);
+    }
+
+    int ensure_resident() override {
+        if (!evicted) return HBEGP_OK;
+        int rc = (nu2 == 5) ? rebuild_nu<5>() : (nu2 == 3) ? rebuild_nu<3>() : rebuild_nu<1>();
+        if (rc == HBEGP_OK) {
+            // it is the most recently used model now: move it to the back and let the policy drop another one
+            auto& ms = eng->models;
+            ms.erase(std::remove(ms.begin(), ms.end(), (Model*)this), ms.end());
+            ms.push_back(this);
+            eng->evict_old_models();
+        }
+        return rc;
+    }
 
     int predict_host(long m, const void* xs, void* mean, void* var, long* n_below) override {
         if (m < 0 || (m > 0 && (!xs || !mean))) return fail(HBEGP_ERR_INVALID, "predict: bad arguments");
@@ -1213,6 +1310,7 @@ int Engine<T>::finish_model(int nu2, Model** out, double* lml, void* alpha_out, 
     if (ce != cudaSuccess) { delete m; return fail(HBEGP_ERR_CUDA, std::string("model_create: ") + cudaGetErrorString(ce)); }
     if (g_trace_model) fprintf(stderr, "[hbegp] finish_model: buffers %.3f ms, copies %.3f ms\n", t1 - t0, now_ms() - t1);
     models.push_back(m);
+    evict_old_models();
     *out = m;
     return HBEGP_OK;
 }
@@ -1308,7 +1406,7 @@ int Engine<T>::model_extend(Model* prior_, Model** out, double* lml, void* alpha
     // the append needs at least one complete 64-row leaf of the prior model and the old rows as a prefix
     // (a multiple of 128 rows of the prior are kept so that the appended blocks stay aligned with the 128-wide tiles)
     int r1 = (int)(std::min<long>(prior->n, n) / (2 * TILE)) * (2 * TILE);
-    if (!prior->w_aligned128) r1 = 0;
+    if (!prior->w_aligned128 || prior->evicted) r1 = 0;  // (an evicted prior would have to be refactorised first: no gain)
     if (prior->n > n || !same_noise) r1 = 0;
     if (r1 > 0) {
         CUDA_TRY(cudaMemcpyAsync(prm.p, h_prm, (size_t)p() * sizeof(T), cudaMemcpyHostToDevice, stream));
@@ -1763,6 +1861,24 @@ int hbegp_ctx_set_workspace_limit(hbegp_ctx* ctx, unsigned long long bytes) {
 
 long long hbegp_ctx_launch_count(hbegp_ctx* ctx) { return ctx ? ctx->eng->launches : 0; }
 
+int hbegp_ctx_set_resident_models(hbegp_ctx* ctx, int max_resident) {
+    if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");
+    ctx->eng->resident_limit = max_resident;
+    ctx->eng->evict_old_models();
+    return HBEGP_OK;
+}
+
+int hbegp_ctx_model_stats(hbegp_ctx* ctx, int* live, int* resident, long long* evictions, long long* rebuilds) {
+    if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");
+    int r = 0;
+    for (Model* m : ctx->eng->models) r += m->evicted ? 0 : 1;
+    if (live) *live = (int)ctx->eng->models.size();
+    if (resident) *resident = r;
+    if (evictions) *evictions = ctx->eng->n_evictions;
+    if (rebuilds) *rebuilds = ctx->eng->n_rebuilds;
+    return HBEGP_OK;
+}
+
 int hbegp_set_data(hbegp_ctx* ctx, long n, int d, const void* x, const void* y) {
     if (!ctx) return fail(HBEGP_ERR_INVALID, "null context");
     return ctx->eng->set_data(n, d, x, y, false);
@@ -1816,6 +1932,7 @@ int hbegp_comm_unique_id(void* id_out) {
 }
 
 static int comm_attach(EngineBase* e, ncclComm_t comm, int rank, int world) {
+    CUDA_TRY(cudaSetDevice(e->device));  // the timing events belong to this context's device
     e->comm = comm;
     e->comm_rank = rank;
     e->comm_world = world;

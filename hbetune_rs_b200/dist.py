@@ -106,6 +106,31 @@ def all_reduce_sum_inplace(values: np.ndarray) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
 
+def init_library_comm(ctx) -> None:
+    """Gives ``ctx`` (this rank's context) the NCCL communicator the library uses for its own exchanges
+    (``hbegp_comm_init``): rank 0 creates the id, ``torch.distributed`` only carries those 128 bytes."""
+    import torch
+    rank, size = world()
+    if size == 1:
+        return
+    dist = _dist()
+    dev = _device()
+    ident = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        ident = torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8).to(dev)
+    dist.broadcast(ident, src=0)
+    ctx.comm_init(size, rank, bytes(ident.cpu().numpy().tobytes()))
+
+
+class LibraryFit:
+    """``shard=`` argument of ``FittedKernel.new``: the balanced restart loop with the per-round exchange done INSIDE
+    libhbegp.so (device-side packing + ncclAllReduce on the communicator of ``init_library_comm``)."""
+
+    def fit_runs(self, ctx, starts, lo, hi, nu=2.5, maxeval=150):
+        rank, size = world()
+        return ctx.fit_runs(starts, lo, hi, nu, maxeval, rank=rank, world=size, allreduce=None)
+
+
 class BalancedFit:
     """``shard=`` argument of ``FittedKernel.new`` / ``EstimatorGPR.shard``: the restart loop balanced per round over
     all ranks (``hbegp_fit_runs_sharded``).  Every rank must hold the same training data and call with the same

@@ -205,6 +205,16 @@ class Context:
     def launch_count(self) -> int:
         return int(lib.hbegp_ctx_launch_count(self._h))
 
+    def set_resident_models(self, max_resident: int):
+        """``hbegp_ctx_set_resident_models``: how many models keep their n x n factor on the device."""
+        check(lib.hbegp_ctx_set_resident_models(self._h, max_resident), "hbegp_ctx_set_resident_models")
+
+    def model_stats(self):
+        live, res = C.c_int(), C.c_int()
+        ev, rb = C.c_longlong(), C.c_longlong()
+        check(lib.hbegp_ctx_model_stats(self._h, C.byref(live), C.byref(res), C.byref(ev), C.byref(rb)), "hbegp_ctx_model_stats")
+        return {"live": live.value, "resident": res.value, "evictions": ev.value, "rebuilds": rb.value}
+
     def set_workspace_limit(self, nbytes: int):
         check(lib.hbegp_ctx_set_workspace_limit(self._h, nbytes), "hbegp_ctx_set_workspace_limit")
 
@@ -232,10 +242,45 @@ class Context:
                                        _ptr(status)), "hbegp_lml_grad_batch")
         return lml, grad, status
 
+    # ---- exchange between GPUs inside the library (NCCL on device buffers)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """``hbegp_comm_unique_id``: 128 bytes rank 0 hands to every rank (over any side channel)."""
+        buf = C.create_string_buffer(128)
+        check(lib.hbegp_comm_unique_id(buf), "hbegp_comm_unique_id")
+        return buf.raw
+
+    def comm_init(self, world: int, rank: int, unique_id: bytes):
+        """``hbegp_comm_init``: joins this context (one per process / GPU) to an NCCL communicator of ``world`` ranks."""
+        check(lib.hbegp_comm_init(self._h, world, rank, C.create_string_buffer(unique_id, 128)), "hbegp_comm_init")
+        self.comm_rank, self.comm_world = rank, world
+
+    def comm_info(self):
+        rank, world, ver = C.c_int(), C.c_int(), C.c_int()
+        ms, cnt = C.c_double(), C.c_longlong()
+        check(lib.hbegp_comm_info(self._h, C.byref(rank), C.byref(world), C.byref(ver), C.byref(ms), C.byref(cnt)), "hbegp_comm_info")
+        return {"rank": rank.value, "world": world.value, "nccl_version": ver.value, "collective_ms": ms.value,
+                "n_collectives": cnt.value}
+
+    def lml_grad_batch_sharded(self, theta: np.ndarray, nu: float = 2.5, lo=None, hi=None, want_grad: bool = True):
+        """``hbegp_lml_grad_batch_sharded``: every rank passes the same thetas and gets all results; rank r evaluates
+        thetas r, r + world, ...; one ncclAllGather of the device-resident records."""
+        theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        B, p = theta.shape
+        lo = None if lo is None else np.ascontiguousarray(lo, dtype=np.float64)
+        hi = None if hi is None else np.ascontiguousarray(hi, dtype=np.float64)
+        lml = np.empty(B)
+        grad = np.empty((B, p)) if want_grad else None
+        status = np.empty(B, dtype=np.int32)
+        check(lib.hbegp_lml_grad_batch_sharded(self._h, nu, B, _ptr(theta), _ptr(lo), _ptr(hi), _ptr(lml), _ptr(grad),
+                                               _ptr(status)), "hbegp_lml_grad_batch_sharded")
+        return lml, grad, status
+
     def fit_runs(self, starts: np.ndarray, lo, hi, nu: float = 2.5, maxeval: int = 150, rank: int = 0, world: int = 1,
                  allreduce=None):
         """``hbegp_fit_runs``; with ``world > 1`` the balanced multi-process loop (``hbegp_fit_runs_sharded``):
-        ``allreduce(array)`` must sum the float64 array in place over all ranks."""
+        ``allreduce(array)`` must sum the float64 array in place over all ranks, or None to let the library exchange
+        the rounds itself over the communicator of ``comm_init`` (ncclAllReduce on the device-resident record)."""
         starts = np.ascontiguousarray(np.atleast_2d(starts), dtype=np.float64)
         R, p = starts.shape
         lo = np.ascontiguousarray(lo, dtype=np.float64)
@@ -246,7 +291,7 @@ class Context:
             check(lib.hbegp_fit_runs(self._h, nu, R, _ptr(starts), _ptr(lo), _ptr(hi), maxeval, res, _ptr(best_theta)),
                   "hbegp_fit_runs")
         else:
-            cb = _lib.allreduce_callback(allreduce)
+            cb = _lib.allreduce_callback(allreduce) if allreduce is not None else _lib.ALLREDUCE_FN()  # NULL: library NCCL
             check(lib.hbegp_fit_runs_sharded(self._h, nu, R, _ptr(starts), _ptr(lo), _ptr(hi), maxeval, rank, world, cb, None,
                                              res, _ptr(best_theta)), "hbegp_fit_runs_sharded")
         return res, best_theta
@@ -339,9 +384,114 @@ class Model:
         k = check(lib.hbegp_predict_warn_values(self._h, cap, _ptr(vals), _ptr(rows)), "hbegp_predict_warn_values")
         return vals[:k], rows[:k]
 
+    def predict_sharded(self, xs: np.ndarray, want_variance: bool = True):
+        """``hbegp_predict_sharded``: every rank passes all rows and gets all results; contiguous row blocks per rank,
+        one ncclAllGather of the device-resident (mean, variance) shards."""
+        xs = np.ascontiguousarray(xs, dtype=self.A)
+        m = xs.shape[0]
+        mean = np.empty(m, dtype=self.A)
+        var = np.empty(m, dtype=self.A) if want_variance else None
+        nb = C.c_long(0)
+        check(lib.hbegp_predict_sharded(self._h, m, _ptr(xs), _ptr(mean), _ptr(var), C.byref(nb)), "hbegp_predict_sharded")
+        self.n_below_warn = nb.value
+        return mean, var
+
     def predict_device(self, m: int, xs_ptr: int, mean_ptr: int, var_ptr: Optional[int] = None):
         check(lib.hbegp_predict_device(self._h, m, C.c_void_p(xs_ptr), C.c_void_p(mean_ptr),
                                        C.c_void_p(var_ptr) if var_ptr else None, None), "hbegp_predict_device")
+
+
+class MultiContext:
+    """``hbegp_multi``: ONE process over several GPUs (the reference is one process, ``src/bin/hbetune/main.rs:255-355``).
+    Thetas / live runs are dealt round-robin to the GPUs, candidate rows go out in contiguous blocks, data and model are
+    replicated with ncclBroadcast; results are bit-identical to one GPU."""
+
+    def __init__(self, n_gpus: int, dtype: int = _lib.F64, devices: Optional[Sequence[int]] = None):
+        self.dtype, self.A = dtype, _np_dtype(dtype)
+        h = C.c_void_p()
+        dev = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        check(lib.hbegp_multi_create(n_gpus, _ptr(dev), dtype, C.byref(h)), "hbegp_multi_create")
+        self._h = h
+        self.n_gpus = n_gpus
+        self.n = self.d = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.hbegp_multi_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        self.close()
+
+    def set_data(self, x, y):
+        x = np.ascontiguousarray(x, dtype=self.A)
+        y = np.ascontiguousarray(y, dtype=self.A)
+        check(lib.hbegp_multi_set_data(self._h, x.shape[0], x.shape[1], _ptr(x), _ptr(y)), "hbegp_multi_set_data")
+        self.n, self.d = x.shape
+
+    def lml_grad_batch(self, theta, nu: float = 2.5, lo=None, hi=None):
+        theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        B, p = theta.shape
+        lo = None if lo is None else np.ascontiguousarray(lo, dtype=np.float64)
+        hi = None if hi is None else np.ascontiguousarray(hi, dtype=np.float64)
+        lml, grad, status = np.empty(B), np.empty((B, p)), np.empty(B, dtype=np.int32)
+        check(lib.hbegp_multi_lml_grad_batch(self._h, nu, B, _ptr(theta), _ptr(lo), _ptr(hi), _ptr(lml), _ptr(grad), _ptr(status)),
+              "hbegp_multi_lml_grad_batch")
+        return lml, grad, status
+
+    def fit_runs(self, starts, lo, hi, nu: float = 2.5, maxeval: int = 150):
+        starts = np.ascontiguousarray(np.atleast_2d(starts), dtype=np.float64)
+        R, p = starts.shape
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        res = (_lib.RunResult * R)()
+        best_theta = np.empty((R, p))
+        check(lib.hbegp_multi_fit_runs(self._h, nu, R, _ptr(starts), _ptr(lo), _ptr(hi), maxeval, res, _ptr(best_theta)),
+              "hbegp_multi_fit_runs")
+        return res, best_theta
+
+    def model(self, theta, nu: float = 2.5, lo=None, hi=None) -> "MultiModel":
+        return MultiModel(self, theta, nu, lo, hi)
+
+
+class MultiModel:
+    """``hbegp_multi_model``: one evaluation on GPU 0, replicas on the other GPUs over NVLink."""
+
+    def __init__(self, mctx: MultiContext, theta, nu=2.5, lo=None, hi=None):
+        self.mctx, self.A, self.d = mctx, mctx.A, mctx.d
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        lo = None if lo is None else np.ascontiguousarray(lo, dtype=np.float64)
+        hi = None if hi is None else np.ascontiguousarray(hi, dtype=np.float64)
+        h, lml = C.c_void_p(), C.c_double()
+        rc = lib.hbegp_multi_model_create(mctx._h, nu, _ptr(theta), _ptr(lo), _ptr(hi), C.byref(h), C.byref(lml), None, None)
+        if rc == _lib.NOT_PD:
+            raise np.linalg.LinAlgError("Kernel matrix must be invertible.")
+        check(rc, "hbegp_multi_model_create")
+        self._h, self.lml = h, lml.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.hbegp_multi_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def predict(self, xs, want_variance: bool = True):
+        xs = np.ascontiguousarray(xs, dtype=self.A)
+        m = xs.shape[0]
+        mean = np.empty(m, dtype=self.A)
+        var = np.empty(m, dtype=self.A) if want_variance else None
+        nb = C.c_long(0)
+        check(lib.hbegp_multi_predict(self._h, m, _ptr(xs), _ptr(mean), _ptr(var), C.byref(nb)), "hbegp_multi_predict")
+        self.n_below_warn = nb.value
+        return mean, var
 
 
 @dataclass

@@ -52,6 +52,14 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out);
 int hbegp_ctx_destroy(hbegp_ctx* ctx);
 /* Caps the device memory the context may use for batched evaluation workspaces (0: default 70% of free). */
 int hbegp_ctx_set_workspace_limit(hbegp_ctx* ctx, unsigned long long bytes);
+/* Retained-model policy.  The reference's minimizer keeps the model of EVERY generation (all_models,
+ * src/core/minimize.rs:331, :407) although only the newest one is asked anything; an n x n factor per generation would
+ * exhaust the device (50 generations at n = 4096: 6.7 GB; two models at n = 16384 fill a GPU).  Only the `max_resident`
+ * most recently created / used models of a context keep their factor on the device (default 4; <= 0: all).  An older
+ * model stays valid and cheap (X^T / l, alpha and the parameters remain: O(n d)); its next variance prediction
+ * refactorises (one n^3 / 3 evaluation) and makes it resident again. */
+int hbegp_ctx_set_resident_models(hbegp_ctx* ctx, int max_resident);
+int hbegp_ctx_model_stats(hbegp_ctx* ctx, int* live, int* resident, long long* evictions, long long* rebuilds);
 /* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
 long long hbegp_ctx_launch_count(hbegp_ctx* ctx);
 

@@ -11,7 +11,6 @@ use ndarray::prelude::*;
 
 use hbegp_sys as ffi;
 
-use crate::core::acquisition::expected_improvement;
 use crate::core::gpr::{estimate_amplitude, Error, EstimatorGPR};       // made pub(crate) in gpr.rs
 use crate::core::surrogate_model::SummaryStatistics;
 use crate::core::ynormalize::YNormalize;
@@ -86,11 +85,59 @@ impl<A: Scalar> SurrogateModelCuda<A> {
             ffi::hbegp_predict(self.device.0, m as c_long, x.as_ptr() as *const c_void,
                                mean.as_mut_ptr() as *mut c_void, var_ptr, &mut below)
         });
-        if below > 0 {
-            // predict.rs:39-46 lists the values; the device path reports how many there were
-            eprintln!("Variances below 0 were predicted and will be corrected: {} value(s)", below);
-        }
+        self.warn_about_negative_variances(below);
         (mean, var)
+    }
+
+    /// src/gpr/predict.rs:39-46: the same stderr message, values from hbegp_predict_warn_values (row order)
+    fn warn_about_negative_variances(&self, below: c_long) {
+        if below <= 0 {
+            return;
+        }
+        let mut vals = vec![0f64; (below as usize).min(4096)];
+        let k = unsafe {
+            ffi::hbegp_predict_warn_values(self.device.0, vals.len() as c_int, vals.as_mut_ptr(), std::ptr::null_mut())
+        };
+        vals.truncate(k.max(0) as usize);
+        eprintln!(
+            "Variances below 0 were predicted and will be corrected: {}",
+            vals.iter().map(|v| format!("{:.2e}", v)).collect::<Vec<_>>().join(", ")
+        );
+    }
+
+    fn y_norm_ffi(&self) -> ffi::hbegp_ynorm {
+        self.y_norm.as_ffi() // amplitude, expected, projection, dtype (ynormalize.rs:7-12)
+    }
+
+    /// find_best_candidate_by_ei (src/core/acquisition.rs:177-202) for all candidates in ONE call: prediction, EI,
+    /// de-normalisation and the arg-max (`max_by`: the LAST maximum wins) on the device.
+    pub fn best_candidate_by_ei(&self, candidates: ArrayView2<A>, fmin: A) -> (usize, A, A) {
+        let x = candidates.as_standard_layout();
+        let m = x.nrows();
+        let (mut mean, mut ei) = (Array1::<A>::zeros(m), Array1::<A>::zeros(m));
+        let (mut best, mut below): (c_long, c_long) = (-1, 0);
+        check(unsafe {
+            ffi::hbegp_predict_mean_ei(self.device.0, &self.y_norm_ffi(), m as c_long, x.as_ptr() as *const c_void,
+                                       fmin.into(), mean.as_mut_ptr() as *mut c_void, ei.as_mut_ptr() as *mut c_void,
+                                       &mut best, &mut below)
+        });
+        self.warn_about_negative_variances(below);
+        let best = best as usize;
+        (best, mean[best], ei[best])
+    }
+
+    /// find_best_individual_by_confidence_bound (src/core/minimize.rs:680-714) over all samples in ONE call
+    /// (strict `<`: the FIRST minimum wins).
+    pub fn best_by_confidence_bound(&self, samples: ArrayView2<A>, cb: A) -> usize {
+        let x = samples.as_standard_layout();
+        let (mut best, mut below): (c_long, c_long) = (-1, 0);
+        check(unsafe {
+            ffi::hbegp_predict_confidence_bound(self.device.0, &self.y_norm_ffi(), x.nrows() as c_long,
+                                                x.as_ptr() as *const c_void, cb.into(), std::ptr::null_mut(), &mut best,
+                                                &mut below)
+        });
+        self.warn_about_negative_variances(below);
+        best as usize
     }
 }
 
@@ -117,17 +164,19 @@ impl<A: Scalar> SurrogateModel<A> for SurrogateModelCuda<A> {
     }
 
     fn predict_mean_ei_a(&self, x: Array2<A>, fmin: A) -> (Array1<A>, Array1<A>) {
-        // gpr.rs:179-212
-        let (y, y_var) = self.predict(x.view(), true);
-        let y_var = y_var.unwrap();
-        let fmin = *self.y_norm.project_into_normalized(array![fmin]).first().unwrap();
-        let mut ei: Array1<A> = Array1::zeros(x.nrows());
-        ndarray::Zip::from(&mut ei).and(&y).and(&y_var).apply(|ei, &y, &var| {
-            *ei = A::from_f(expected_improvement(y.into(), var.sqrt().into(), fmin.into()))
+        // gpr.rs:179-212 in ONE call: prediction, projection of fmin into normalised space (:192-196), per-row
+        // expected_improvement in f64 (acquisition.rs:141-171) and de-normalisation of the mean (:210) on the device
+        let x = x.as_standard_layout();
+        let m = x.nrows();
+        let (mut mean, mut ei) = (Array1::<A>::zeros(m), Array1::<A>::zeros(m));
+        let mut below: c_long = 0;
+        check(unsafe {
+            ffi::hbegp_predict_mean_ei(self.device.0, &self.y_norm_ffi(), m as c_long, x.as_ptr() as *const c_void,
+                                       fmin.into(), mean.as_mut_ptr() as *mut c_void, ei.as_mut_ptr() as *mut c_void,
+                                       std::ptr::null_mut(), &mut below)
         });
-        (self.y_norm.project_location_from_normalized(y), ei)
-        // large candidate sets: hbegp_predict_mean_ei does the whole of this method, and
-        // find_best_candidate_by_ei's argmax (acquisition.rs:177-202), on the device in one call.
+        self.warn_about_negative_variances(below);
+        (mean, ei)
     }
 }
 

@@ -24,6 +24,19 @@ pub struct hbegp_ctx {
 pub struct hbegp_model {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct hbegp_batcher {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct hbegp_multi {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct hbegp_multi_model {
+    _private: [u8; 0],
+}
+pub const HBEGP_COMM_ID_BYTES: usize = 128;
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
@@ -90,6 +103,75 @@ extern "C" {
     ) -> c_int;
     pub fn hbegp_pick_best_run(n_runs: c_int, results: *const hbegp_run_result) -> c_int;
 
+    // batched objective for a caller-owned optimiser (NLopt, src/util/gradmin.rs:35-60)
+    pub fn hbegp_batcher_create(
+        ctx: *mut hbegp_ctx, nu: c_double, n_runs: c_int, bounds_lo: *const c_double, bounds_hi: *const c_double,
+        out: *mut *mut hbegp_batcher,
+    ) -> c_int;
+    pub fn hbegp_batcher_eval(
+        batcher: *mut hbegp_batcher, run: c_int, theta: *const c_double, lml: *mut c_double, grad: *mut c_double,
+        status: *mut c_int,
+    ) -> c_int;
+    pub fn hbegp_batcher_leave(batcher: *mut hbegp_batcher, run: c_int, final_f: c_double) -> c_int;
+    pub fn hbegp_batcher_results(
+        batcher: *mut hbegp_batcher, results: *mut hbegp_run_result, best_theta: *mut c_double, n_rounds: *mut c_longlong,
+    ) -> c_int;
+    pub fn hbegp_batcher_destroy(batcher: *mut hbegp_batcher) -> c_int;
+    pub fn hbegp_lbfgs_set_tolerances(ftol: c_double, gtol: c_double) -> c_int;
+
+    // exchange between GPUs inside the library (NCCL)
+    pub fn hbegp_comm_unique_id(id_out: *mut c_void) -> c_int; // 128 bytes
+    pub fn hbegp_comm_init(ctx: *mut hbegp_ctx, world: c_int, rank: c_int, id: *const c_void) -> c_int;
+    pub fn hbegp_comm_info(
+        ctx: *mut hbegp_ctx, rank: *mut c_int, world: *mut c_int, nccl_version: *mut c_int, collective_ms: *mut c_double,
+        n_collectives: *mut c_longlong,
+    ) -> c_int;
+    pub fn hbegp_lml_grad_batch_sharded(
+        ctx: *mut hbegp_ctx, nu: c_double, b: c_int, theta: *const c_double, lo: *const c_double, hi: *const c_double,
+        lml: *mut c_double, grad: *mut c_double, status: *mut c_int,
+    ) -> c_int;
+    pub fn hbegp_multi_create(n_gpus: c_int, devices: *const c_int, dtype: c_int, out: *mut *mut hbegp_multi) -> c_int;
+    pub fn hbegp_multi_destroy(multi: *mut hbegp_multi) -> c_int;
+    pub fn hbegp_multi_n_gpus(multi: *const hbegp_multi) -> c_int;
+    pub fn hbegp_multi_ctx(multi: *mut hbegp_multi, i: c_int) -> *mut hbegp_ctx;
+    pub fn hbegp_multi_set_data(multi: *mut hbegp_multi, n: c_long, d: c_int, x: *const c_void, y: *const c_void) -> c_int;
+    pub fn hbegp_multi_lml_grad_batch(
+        multi: *mut hbegp_multi, nu: c_double, b: c_int, theta: *const c_double, lo: *const c_double, hi: *const c_double,
+        lml: *mut c_double, grad: *mut c_double, status: *mut c_int,
+    ) -> c_int;
+    pub fn hbegp_multi_fit_runs(
+        multi: *mut hbegp_multi, nu: c_double, n_runs: c_int, starts: *const c_double, bounds_lo: *const c_double,
+        bounds_hi: *const c_double, maxeval: c_int, results: *mut hbegp_run_result, best_theta: *mut c_double,
+    ) -> c_int;
+    pub fn hbegp_multi_model_create(
+        multi: *mut hbegp_multi, nu: c_double, theta: *const c_double, lo: *const c_double, hi: *const c_double,
+        out: *mut *mut hbegp_multi_model, lml: *mut c_double, alpha_out: *mut c_void, kinv_out: *mut c_void,
+    ) -> c_int;
+    pub fn hbegp_multi_model_destroy(model: *mut hbegp_multi_model) -> c_int;
+    pub fn hbegp_multi_model_replica(model: *mut hbegp_multi_model, i: c_int) -> *mut hbegp_model;
+    pub fn hbegp_multi_predict(
+        model: *mut hbegp_multi_model, m: c_long, xs: *const c_void, mean: *mut c_void, var: *mut c_void,
+        n_below_warn: *mut c_long,
+    ) -> c_int;
+
+    // retained-model policy
+    pub fn hbegp_ctx_set_resident_models(ctx: *mut hbegp_ctx, max_resident: c_int) -> c_int;
+    pub fn hbegp_ctx_model_stats(
+        ctx: *mut hbegp_ctx, live: *mut c_int, resident: *mut c_int, evictions: *mut c_longlong, rebuilds: *mut c_longlong,
+    ) -> c_int;
+
+    // trait Kernel standalone (src/gpr/kernel.rs:8-43)
+    pub fn hbegp_kernel_matrix(
+        ctx: *mut hbegp_ctx, nu: c_double, d: c_int, theta: *const c_double, n1: c_long, x1: *const c_void, n2: c_long,
+        x2: *const c_void, k_out: *mut c_void,
+    ) -> c_int;
+    pub fn hbegp_kernel_theta_grad(
+        ctx: *mut hbegp_ctx, nu: c_double, d: c_int, theta: *const c_double, n: c_long, x: *const c_void, k_out: *mut c_void,
+        grad_out: *mut c_void,
+    ) -> c_int;
+    pub fn hbegp_kernel_diag(dtype: c_int, d: c_int, theta: *const c_double, n: c_long, diag_out: *mut c_void) -> c_int;
+    pub fn hbegp_debug_poison(ctx: *mut hbegp_ctx) -> c_int;
+
     pub fn hbegp_model_create(
         ctx: *mut hbegp_ctx, nu: c_double, theta: *const c_double, lo: *const c_double, hi: *const c_double,
         out: *mut *mut hbegp_model, lml: *mut c_double, alpha_out: *mut c_void, kinv_out: *mut c_void,
@@ -105,6 +187,10 @@ extern "C" {
     pub fn hbegp_predict(
         model: *mut hbegp_model, m: c_long, xs: *const c_void, mean: *mut c_void, var: *mut c_void,
         n_below_warn: *mut c_long,
+    ) -> c_int;
+    pub fn hbegp_predict_warn_values(model: *const hbegp_model, cap: c_int, values_out: *mut c_double, rows_out: *mut c_long) -> c_int;
+    pub fn hbegp_predict_sharded(
+        model: *mut hbegp_model, m: c_long, xs: *const c_void, mean: *mut c_void, var: *mut c_void, n_below_warn: *mut c_long,
     ) -> c_int;
     pub fn hbegp_predict_device(
         model: *mut hbegp_model, m: c_long, xs_device: *const c_void, mean_device: *mut c_void,
