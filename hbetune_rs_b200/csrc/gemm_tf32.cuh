@@ -20,10 +20,11 @@
 //   warp 1   MMA issuer: one elected lane issues 4 k steps x 3 tcgen05.mma (M = 128, N = 128, K = 8) per stage from
 //            shared-memory descriptors (K-major SWIZZLE_128B or MN-major SWIZZLE_128B_BASE32B) and commits the stage back to the
 //            producer; after the last stage it commits to the epilogue barrier;
-//   warps 6-9 drain + epilogue: the tensor core's FP32 accumulation truncates (a bias that grows linearly with k), so the
-//            hi*hi sum is kept in TMEM for 64 k at a time (two alternating 128-column buffers) and each finished chunk
-//            is added round-to-nearest into registers with tcgen05.ld (one output row per thread); at the end the small
-//            terms are added, then alpha / beta and the masked store (or the row sums of squares).
+//   warps 6-9 drain + epilogue: the tensor core's FP32 accumulation truncates (a systematic bias), so the hi*hi term is
+//            never accumulated in TMEM: each k step's product lands in one of three rotating 128-column buffers and is
+//            added round-to-nearest into registers with tcgen05.ld (one output row per thread); at the end the small
+//            terms (accumulated in TMEM: their bias is 2^-11 of that) are added, then alpha / beta and the masked
+//            store (or the row sums of squares).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -38,8 +39,8 @@ constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;  // 16 KB: one operand tile (hi or lo)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // A_hi, A_lo, B_hi, B_lo
 constexpr int THREADS = 320;
-constexpr int CHUNK = 2;        // k-blocks (of BK) accumulated in TMEM before the partial sum is drained into registers
-constexpr int TMEM_COLS = 512;  // 2 x 128 columns of chunk accumulators + 128 for the small terms (power of two)
+constexpr int NBUF = 3;         // TMEM buffers the hi*hi products of successive k steps rotate through
+constexpr int TMEM_COLS = 512;  // NBUF x 128 columns of per-k-step products + 128 for the small-term accumulator
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 
 struct Params {
@@ -175,9 +176,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
     uint64_t* full = bars;                 // TMA landed
     uint64_t* xf = bars + STAGES;          // transform done
     uint64_t* empty = bars + 2 * STAGES;   // MMAs of the stage retired
-    uint64_t* accf = bars + 3 * STAGES;    // [2] the chunk accumulated in `big` buffer b is complete
-    uint64_t* acce = accf + 2;             // [2] buffer b has been drained into registers
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce + 2);
+    uint64_t* accf = bars + 3 * STAGES;    // [NBUF] the product of one k step has landed in TMEM buffer b
+    uint64_t* acce = accf + NBUF;          // [NBUF] buffer b has been added into the registers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce + NBUF);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
     else if (p.kmode == K_LE_M) kend = min(p.K, m0 + BM);
     else if (p.kmode == K_GE_M) kbeg = m0;
     const int nk = (kend - kbeg) / BK;
-    const int nchunks = (nk + CHUNK - 1) / CHUNK;
+    constexpr int KSTEPS = BK / 8;  // tcgen05.mma kind::tf32 has K = 8
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
             mbar_init(&xf[s], 4);
             mbar_init(&empty[s], 1);
         }
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < NBUF; b++) {
             mbar_init(&accf[b], 1);
             mbar_init(&acce[b], 4);
         }
@@ -215,8 +216,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    // TMEM columns: [0, 128) and [128, 256) the two `big` chunk accumulators, [256, 384) the `small` accumulator
-    const uint32_t d_small = tmem_base + 2 * BN;
+    // TMEM columns: NBUF buffers of 128 for the hi*hi product of one k step each, then 128 for the `small` accumulator
+    const uint32_t d_small = tmem_base + NBUF * BN;
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
@@ -256,29 +257,26 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
             constexpr uint32_t a_lay = A_KMAJOR ? 2 : 1, b_lay = B_KMAJOR ? 2 : 1;
             for (int kt = 0; kt < nk; kt++) {
                 const int s = kt % STAGES;
-                const int c = kt / CHUNK, buf = c & 1;
-                const bool chunk_first = (kt % CHUNK) == 0, chunk_last = (kt % CHUNK) == CHUNK - 1 || kt == nk - 1;
-                if (chunk_first) {  // the buffer's previous chunk must have been drained (first two uses pass at once)
-                    mbar_wait(&acce[buf], ((c >> 1) & 1) ^ 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-                const uint32_t d_big = tmem_base + buf * BN;
                 mbar_wait(&xf[s], (kt / STAGES) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE_BYTES), a_lo = a_hi + TILE_BYTES;
                 const uint32_t b_hi = a_hi + 2 * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
 #pragma unroll
-                for (int ks = 0; ks < BK / 8; ks++) {
+                for (int ks = 0; ks < KSTEPS; ks++) {
+                    const int g = kt * KSTEPS + ks, buf = g % NBUF, use = g / NBUF;
+                    // the buffer's previous product must have been added into the registers (first NBUF uses pass at once)
+                    mbar_wait(&acce[buf], (use & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t dah = make_desc(a_hi + ks * a_kstep, a_lbo, a_sbo, a_lay);
                     const uint64_t dal = make_desc(a_lo + ks * a_kstep, a_lbo, a_sbo, a_lay);
                     const uint64_t dbh = make_desc(b_hi + ks * b_kstep, b_lbo, b_sbo, b_lay);
                     const uint64_t dbl = make_desc(b_lo + ks * b_kstep, b_lbo, b_sbo, b_lay);
-                    mma_tf32(d_small, dal, dbh, idesc, (kt > 0 || ks > 0) ? 1u : 0u);
+                    mma_tf32(d_small, dal, dbh, idesc, g > 0 ? 1u : 0u);
                     mma_tf32(d_small, dah, dbl, idesc, 1u);
-                    mma_tf32(d_big, dah, dbh, idesc, (!chunk_first || ks > 0) ? 1u : 0u);
+                    mma_tf32(tmem_base + buf * BN, dah, dbh, idesc, 0u);  // a fresh product every k step: no accumulation in TMEM
+                    mma_commit(&accf[buf]);
                 }
                 mma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
-                if (chunk_last) mma_commit(&accf[buf]);
             }
         }
     } else if (warp < 6) {
@@ -310,20 +308,24 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
         }
     } else {
         // ---------------------------------------------------------------- drain + epilogue (warps 6..9)
-        // The tensor core adds into its FP32 accumulator with truncation, a bias of ~2^-24 per accumulation that grows
-        // linearly with k (probe: 2.7e-5 relative at k = 4096 on positive data).  So the hi*hi products are accumulated
-        // in TMEM over CHUNK k-blocks only; each finished chunk is added, round-to-nearest, into registers here while the
-        // tensor core fills the other buffer.  One output row per thread (a warp may touch TMEM lanes
-        // 32 * (warp % 4) .. + 31 only), 128 columns in registers.
+        // The tensor core adds into its FP32 accumulator with TRUNCATION: a bias of ~2^-24 of the running sum per
+        // accumulation, always the same sign.  Accumulating k = 4096 in TMEM loses 2.7e-5 on positive data (probe), and
+        // even 64-k chunks (2e-7, less than the FFMA kernel's random rounding error) cost the f32 Cholesky its
+        // positive-definiteness margin, because a systematic error does not average out over the recursion
+        // (tests/probes/f32_pd_boundary2.py: K stopped factoring at 4x the noise level the FFMA path reaches).  So
+        // nothing is accumulated in TMEM for the hi*hi term: every k step (k = 8) writes a fresh product into one of NBUF
+        // rotating buffers and is added round-to-nearest into registers here while the tensor core fills the next.
+        // One output row per thread (a warp may touch TMEM lanes 32 * (warp % 4) .. + 31 only), 128 columns in registers.
         const int lane_base = 32 * (warp & 3);
         const int row = m0 + lane_base + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)lane_base << 16);
         float acc[BN];
 #pragma unroll
         for (int j = 0; j < BN; j++) acc[j] = 0.f;
-        for (int c = 0; c < nchunks; c++) {
-            const int buf = c & 1;
-            mbar_wait(&accf[buf], (c >> 1) & 1);
+        const int nsteps = nk * KSTEPS;
+        for (int g = 0; g < nsteps; g++) {
+            const int buf = g % NBUF;
+            mbar_wait(&accf[buf], (g / NBUF) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive(&acce[buf]);
         }
-        // every MMA has retired (the last chunk's commit covers the small-term products too)
+        // every MMA has retired (the last k step's commit covers the small-term products too)
         const bool row_ok = row < p.M;
         float sumsq = 0.f;
         float* crow = p.C ? p.C + (long)bz * p.sC + (long)row * p.ldc + n0 : nullptr;
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
         for (int c0 = 0; c0 < BN; c0 += 32) {
             float small[32];
             if (nk > 0) {
-                tmem_ld32(lane_addr + 2 * BN + c0, small);
+                tmem_ld32(lane_addr + NBUF * BN + c0, small);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             } else {
 #pragma unroll
@@ -453,6 +455,12 @@ inline bool& enabled() {
     static bool on = true;
     return on;
 }
+// bit i set: GEMM class i may use the tensor path (0 panel solve, 1 T = L21 W11, 2 trailing update, 3 W21 = -W22 T,
+// 4 K^-1 = W^T W, 5 predictive variance); a diagnostic switch (HBEGP_TF32_MASK)
+inline int& class_mask() {
+    static int v = 0x3f;
+    return v;
+}
 inline int& min_extent() {
     static int v = 256;
     return v;
@@ -463,17 +471,18 @@ inline int& min_extent() {
 // Dispatch used by the engine: f64 -> DMMA kernel; f32 -> tcgen05 3xTF32 when the policy allows and the operands meet
 // the 128-wide-tile invariant (`aligned128`: every 128-wide diagonal block of a triangular operand has exact zeros
 // above its diagonal), else the FFMA kernel.
-template <typename T, bool AK, bool BKM>
-inline cudaError_t launch_gemm_auto(const GemmArgs<T>& a, int batch, cudaStream_t stream, bool aligned128) {
-    if constexpr (std::is_same<T, float>::value) {
-        if (tf32::enabled() && aligned128 && (a.M < a.N ? a.M : a.N) >= tf32::min_extent()) return tf32::launch<AK, BKM>(a, batch, stream);
-    }
-    return launch_gemm<T, AK, BKM>(a, batch, stream);
+template <typename T>
+inline bool gemm_uses_tf32(int M, int N, bool aligned128, int cls) {
+    return std::is_same<T, float>::value && tf32::enabled() && aligned128 && (M < N ? M : N) >= tf32::min_extent() &&
+           ((tf32::class_mask() >> cls) & 1);
 }
 
-template <typename T>
-inline bool gemm_uses_tf32(int M, int N, bool aligned128) {
-    return std::is_same<T, float>::value && tf32::enabled() && aligned128 && (M < N ? M : N) >= tf32::min_extent();
+template <typename T, bool AK, bool BKM>
+inline cudaError_t launch_gemm_auto(const GemmArgs<T>& a, int batch, cudaStream_t stream, bool aligned128, int cls) {
+    if constexpr (std::is_same<T, float>::value) {
+        if (gemm_uses_tf32<T>(a.M, a.N, aligned128, cls)) return tf32::launch<AK, BKM>(a, batch, stream);
+    }
+    return launch_gemm<T, AK, BKM>(a, batch, stream);
 }
 
 }  // namespace hbegp

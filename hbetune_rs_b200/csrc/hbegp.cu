@@ -492,7 +492,7 @@ struct Engine : EngineBase {
         // 1. panel solve as a product with the inverse: L21 = A21 W11^T  -> W(2,1)
         g.A = A21; g.B = W11; g.C = W21; g.M = s2; g.N = s1; g.K = s1; g.kmode = K_LE_N; g.lower_only = 0;
         g.alpha = T(1); g.beta = T(0);
-        CUDA_TRY((launch_gemm_auto<T, true, true>(g, cnt, st, aligned128()))); launches++;
+        CUDA_TRY((launch_gemm_auto<T, true, true>(g, cnt, st, aligned128(), 0))); launches++;
         // 3. T = L21 W11 -> A(2,1); independent of step 2 and of the second half, so it may run on the side stream
         cudaStream_t st3 = st;
         if (sd.st) {
@@ -502,19 +502,19 @@ struct Engine : EngineBase {
         }
         g.A = W21; g.B = W11; g.C = A21; g.M = s2; g.N = s1; g.K = s1; g.kmode = K_GE_N; g.lower_only = 0;
         g.alpha = T(1); g.beta = T(0);
-        CUDA_TRY((launch_gemm_auto<T, true, false>(g, cnt, st3, aligned128()))); launches++;
+        CUDA_TRY((launch_gemm_auto<T, true, false>(g, cnt, st3, aligned128(), 1))); launches++;
         if (sd.st) CUDA_TRY(cudaEventRecord(sd.b, sd.st));
         // 2. trailing update: A22 -= L21 L21^T (lower tiles)
         g.A = W21; g.B = W21; g.C = A22; g.M = s2; g.N = s2; g.K = s1; g.kmode = K_FULL; g.lower_only = 1;
         g.alpha = T(-1); g.beta = T(1);
-        CUDA_TRY((launch_gemm_auto<T, true, true>(g, cnt, st, aligned128()))); launches++;
+        CUDA_TRY((launch_gemm_auto<T, true, true>(g, cnt, st, aligned128(), 2))); launches++;
         if ((rc = chol_inv(st, s0, cnt, r0 + s1, s2, sd))) return rc;
         // (a nested node may have re-recorded sd.b later on the side stream: waiting for that implies our product)
         if (sd.st) CUDA_TRY(cudaStreamWaitEvent(st, sd.b, 0));
         // 4. W21 = -W22 T
         g.A = W22; g.B = A21; g.C = W21; g.M = s2; g.N = s1; g.K = s2; g.kmode = K_LE_M; g.lower_only = 0;
         g.alpha = T(-1); g.beta = T(0);
-        CUDA_TRY((launch_gemm_auto<T, true, false>(g, cnt, st, aligned128()))); launches++;
+        CUDA_TRY((launch_gemm_auto<T, true, false>(g, cnt, st, aligned128(), 3))); launches++;
         return HBEGP_OK;
     }
 
@@ -526,7 +526,7 @@ struct Engine : EngineBase {
         g.A = Wb; g.B = Wb; g.C = Ab; g.M = np; g.N = np; g.K = np; g.kmode = K_GE_M; g.lower_only = 1;
         g.alpha = T(1); g.beta = T(0);
         g.rowsumsq = nullptr;
-        CUDA_TRY((launch_gemm_auto<T, false, false>(g, cnt, st, aligned128()))); launches++;
+        CUDA_TRY((launch_gemm_auto<T, false, false>(g, cnt, st, aligned128(), 4))); launches++;
         return HBEGP_OK;
     }
 
@@ -966,7 +966,7 @@ struct ModelT : Model {
         for (long row0 = 0; row0 < m; row0 += chunk) {
             const int rows = (int)std::min<long>(chunk, round_up(m - row0, 128));
             // column-tile width of the variance GEMM: must be the one launch_gemm_auto picks for exactly this shape
-            const bool tf = gemm_uses_tf32<T>(rows, np, w_aligned128);
+            const bool tf = gemm_uses_tf32<T>(rows, np, w_aligned128, 5);
             const int bn = tf ? 128 : pick_gemm_tile<T>(128, np);  // rows are always a multiple of 128
             const int ntile = (np + bn - 1) / bn;
             T* pm = nullptr;
@@ -987,7 +987,7 @@ struct ModelT : Model {
             g.rowsumsq = (T*)part.p; g.ld_rs = ntile; g.s_rs = 0;
             // keep ~48 MB of k* rows resident in L2 while W streams (ncu before: 35 GB of DRAM reads per 1 GB chunk)
             g.raster_group = (int)std::max<size_t>(1, ((size_t)48 << 20) / ((size_t)bn * np * sizeof(T)));
-            CUDA_TRY((launch_gemm_auto<T, true, true>(g, 1, st, w_aligned128)));
+            CUDA_TRY((launch_gemm_auto<T, true, true>(g, 1, st, w_aligned128, 5)));
             e->launches++;
             k_var_finish<T><<<(rows + 255) / 256, 256, 0, st>>>((const T*)part.p, ntile, ntile, rows, m, row0, (T)c, var, nb, pm, ns, rows, mean,
                                                                 (long*)warn_rows.p, (T*)warn_vals.p, kWarnCap);
@@ -1771,6 +1771,8 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
         const char* tm = getenv("HBEGP_TF32_MIN");
         tf32::enabled() = !(t && atoi(t) == 0);
         tf32::min_extent() = tm ? std::max(64, atoi(tm)) : 256;
+        if (const char* cm = getenv("HBEGP_TF32_MASK")) tf32::class_mask() = atoi(cm);
+        else tf32::class_mask() = 0x3f;
         if (dtype == HBEGP_F32 && tf32::enabled() && !tf32::encode_fn()) {
             delete e;
             return fail(HBEGP_ERR_CUDA, "ctx_create: cuTensorMapEncodeTiled is not available from this driver (set HBEGP_TF32=0)");

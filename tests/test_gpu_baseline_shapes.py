@@ -336,10 +336,11 @@ def test_f32_north_star_optimum_is_the_precisions_own():
         assert rec["oracle_f64"] is not None and rec["cuda_f64_status"] == 0
         assert abs(rec["cuda_f64"] - rec["oracle_f64"]) <= 1e-9 * abs(rec["oracle_f64"]), rec
         if rec["oracle_f32"] is not None:
-            # where single precision still factors K, its LML is only as good as kappa(K) * eps_f32 allows: the two f32
-            # evaluations must agree to the 1e-4 tolerance OR be closer to each other than either is to the f64 value
-            d_impl = abs(rec["cuda_f32"] - rec["oracle_f32"])
-            d_prec = min(abs(rec["cuda_f32"] - rec["oracle_f64"]), abs(rec["oracle_f32"] - rec["oracle_f64"]))
-            assert d_impl <= max(1e-4 * abs(rec["oracle_f32"]), 0.5 * d_prec), rec
+            # where single precision still factors K, its LML is only as good as kappa(K) * eps_f32 allows (the f32 oracle
+            # -- LAPACK spotrf / spotri -- is itself 10 % off the f64 value at the f32 optimum): the CUDA f32 value must
+            # agree with the f32 oracle to the 1e-4 tolerance OR be at least as close to the f64 truth as that oracle is
+            err_cuda = abs(rec["cuda_f32"] - rec["oracle_f64"])
+            err_oracle = abs(rec["oracle_f32"] - rec["oracle_f64"])
+            assert (abs(rec["cuda_f32"] - rec["oracle_f32"]) <= 1e-4 * abs(rec["oracle_f32"])) or err_cuda <= 1.05 * err_oracle, rec
     # each precision's fit must not be beaten, in its own arithmetic, by the other precision's optimum
     assert out["at_f64_optimum"]["cuda_f64"] >= out["at_f32_optimum"]["cuda_f64"] - 1e-6 * abs(out["at_f64_optimum"]["cuda_f64"])

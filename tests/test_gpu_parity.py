@@ -198,8 +198,9 @@ def test_small_batch_predict_path_matches_throughput_path_and_oracle(A):
             mean, var = model.predict(xs[:m])
             np.testing.assert_allclose(mean, mean_ref[:m], rtol=0, atol=tol * max(1.0, np.abs(mean_ref).max()))
             np.testing.assert_allclose(var, var_ref[:m], rtol=0, atol=tol * (c + 1e-5))
+            # the two paths sum in different orders (f32: FFMA mat-vec vs the 3xTF32 tensor GEMM): a few ulps of c
             np.testing.assert_allclose(mean, mean_big[:m], rtol=0, atol=tol * 1e-2 * max(1.0, np.abs(mean_ref).max()))
-            np.testing.assert_allclose(var, var_big[:m], rtol=0, atol=tol * 1e-2 * (c + 1e-5))
+            np.testing.assert_allclose(var, var_big[:m], rtol=0, atol=tol * (1e-2 if A == np.float64 else 5e-2) * (c + 1e-5))
             mean_only, none = model.predict(xs[:m], want_variance=False)
             np.testing.assert_array_equal(mean_only, mean)
             assert none is None
