@@ -245,17 +245,24 @@ def main():
         ctx.set_data(x_pin, y_pin)  # host -> device copy of X, y every step (theta goes up / results come back inside)
         return step_resident()
 
-    def timed(fn, steps, warmup):
+    coll = {"ms": 0.0, "n": 0}
+
+    def timed(fn, steps, warmup, note_collectives=False):
         for _ in range(warmup):
             fn()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ctx.launch_count
+        ci0 = ctx.comm_info()
         e0.record()
         for _ in range(steps):
             out = fn()
         e1.record()
         barrier()
+        if note_collectives:  # device time of the library's NCCL calls inside the timed steps only (warm-up pays NCCL's lazy set-up)
+            ci1 = ctx.comm_info()
+            coll["ms"] = ci1["collective_ms"] - ci0["collective_ms"]
+            coll["n"] = ci1["n_collectives"] - ci0["n_collectives"]
         return max_over_ranks(e0.elapsed_time(e1)) / steps, ctx.launch_count - l0, out
 
     sampler = ClockSampler(local_rank)
@@ -269,11 +276,8 @@ def main():
         ctx.close()
         return
     if args.only != "predict":
-        c0 = ctx.comm_info()
-        ms_step, launches, gathered = timed(step_resident, args.steps, args.warmup)
-        c1 = ctx.comm_info()
-        n_coll = max(1, c1["n_collectives"] - c0["n_collectives"])
-        coll_ms_step = (c1["collective_ms"] - c0["collective_ms"]) / n_coll if world > 1 else 0.0
+        ms_step, launches, gathered = timed(step_resident, args.steps, args.warmup, note_collectives=True)
+        coll_ms_step = coll["ms"] / max(1, coll["n"]) if world > 1 else 0.0
         ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
 
     # ---- prediction: mean + variance of m candidates, rows sharded over ranks
@@ -441,7 +445,8 @@ def main():
             "gpu_launches": int(launches),
             "collective": {"ms_per_step": coll_ms_step, "compute_ms_per_step": ms_step - coll_ms_step, "nccl": ctx.comm_info()["nccl_version"],
                            "ranks": ctx.comm_info()["world"],
-                           "what": "device time of the ncclAllGather of one step (CUDA events around the call, rank 0) vs the rest of the step"},
+                           "what": "device time of the ncclAllGather of one step on rank 0 (CUDA events around the call; it includes waiting "
+                                   "for the slowest rank to arrive) vs the rest of the step"},
             "clocks": clocks,
             "predict": {"candidates_per_s": m / (ms_pred * 1e-3), "ms": ms_pred, "m": m,
                         "e2e_candidates_per_s": m / (ms_pred_e2e * 1e-3), "e2e_ms": ms_pred_e2e,
