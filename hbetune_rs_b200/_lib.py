@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhbegp.so")
+LIB_PATH = os.environ.get("HBEGP_LIB") or os.path.join(_HERE, "libhbegp.so")  # HBEGP_LIB: A/B builds of the same library
 
 F64, F32 = 0, 1
 OK, NOT_PD = 0, 1

@@ -21,7 +21,7 @@
 //            shared-memory descriptors (K-major SWIZZLE_128B or MN-major SWIZZLE_128B_BASE32B) and commits the stage back to the
 //            producer; after the last stage it commits to the epilogue barrier;
 //   warps 6-9 drain + epilogue: the tensor core's FP32 accumulation truncates (a systematic bias), so the hi*hi term is
-//            never accumulated in TMEM: each k step's product lands in one of three rotating 128-column buffers and is
+//            not accumulated in TMEM beyond 16 k: the products land in one of three rotating 128-column buffers and are
 //            added round-to-nearest into registers with tcgen05.ld (one output row per thread); at the end the small
 //            terms (accumulated in TMEM: their bias is 2^-11 of that) are added, then alpha / beta and the masked
 //            store (or the row sums of squares).
@@ -40,6 +40,13 @@ constexpr int TILE_BYTES = BM * BK * 4;  // 16 KB: one operand tile (hi or lo)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // A_hi, A_lo, B_hi, B_lo
 constexpr int THREADS = 320;
 constexpr int NBUF = 3;         // TMEM buffers the hi*hi products of successive k steps rotate through
+#ifndef HBEGP_TF32_KS_PER_BUF
+#define HBEGP_TF32_KS_PER_BUF 2
+#endif
+// k steps (of 8) whose products share a TMEM buffer before it is drained.  1 = no accumulation in TMEM at all; 2 = one
+// truncating accumulation per 16 k.  Measured (profiles/r02_tf32_accumulation.md): 2 keeps the positive-definiteness margin
+// and the fitted optimum of 1 while halving the MMA <-> drain hand-shakes (113 -> 135 TFLOP/s); 8 and more lose the margin.
+constexpr int KS_PER_BUF = HBEGP_TF32_KS_PER_BUF;
 constexpr int TMEM_COLS = 512;  // NBUF x 128 columns of per-k-step products + 128 for the small-term accumulator
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 
@@ -263,18 +270,21 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
                 const uint32_t b_hi = a_hi + 2 * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
 #pragma unroll
                 for (int ks = 0; ks < KSTEPS; ks++) {
-                    const int g = kt * KSTEPS + ks, buf = g % NBUF, use = g / NBUF;
-                    // the buffer's previous product must have been added into the registers (first NBUF uses pass at once)
-                    mbar_wait(&acce[buf], (use & 1) ^ 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const int g = kt * KSTEPS + ks, grp = g / KS_PER_BUF, buf = grp % NBUF, use = grp / NBUF;
+                    const bool first = (g % KS_PER_BUF) == 0, last = (g % KS_PER_BUF) == KS_PER_BUF - 1 || g == nk * KSTEPS - 1;
+                    if (first) {
+                        // the buffer's previous product must have been added into the registers (first NBUF uses pass at once)
+                        mbar_wait(&acce[buf], (use & 1) ^ 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
                     const uint64_t dah = make_desc(a_hi + ks * a_kstep, a_lbo, a_sbo, a_lay);
                     const uint64_t dal = make_desc(a_lo + ks * a_kstep, a_lbo, a_sbo, a_lay);
                     const uint64_t dbh = make_desc(b_hi + ks * b_kstep, b_lbo, b_sbo, b_lay);
                     const uint64_t dbl = make_desc(b_lo + ks * b_kstep, b_lbo, b_sbo, b_lay);
                     mma_tf32(d_small, dal, dbh, idesc, g > 0 ? 1u : 0u);
                     mma_tf32(d_small, dah, dbl, idesc, 1u);
-                    mma_tf32(tmem_base + buf * BN, dah, dbh, idesc, 0u);  // a fresh product every k step: no accumulation in TMEM
-                    mma_commit(&accf[buf]);
+                    mma_tf32(tmem_base + buf * BN, dah, dbh, idesc, first ? 0u : 1u);  // fresh product per buffer use
+                    if (last) mma_commit(&accf[buf]);
                 }
                 mma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
             }
@@ -313,8 +323,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
         // even 64-k chunks (2e-7, less than the FFMA kernel's random rounding error) cost the f32 Cholesky its
         // positive-definiteness margin, because a systematic error does not average out over the recursion
         // (tests/probes/f32_pd_boundary2.py: K stopped factoring at 4x the noise level the FFMA path reaches).  So
-        // nothing is accumulated in TMEM for the hi*hi term: every k step (k = 8) writes a fresh product into one of NBUF
-        // rotating buffers and is added round-to-nearest into registers here while the tensor core fills the next.
+        // (almost) nothing is accumulated in TMEM for the hi*hi term: every KS_PER_BUF k steps (k = 16) start a fresh product
+        // in one of NBUF rotating buffers, which is added round-to-nearest into registers here while the tensor core
+        // fills the next.
         // One output row per thread (a warp may touch TMEM lanes 32 * (warp % 4) .. + 31 only), 128 columns in registers.
         const int lane_base = 32 * (warp & 3);
         const int row = m0 + lane_base + lane;
@@ -322,7 +333,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
         float acc[BN];
 #pragma unroll
         for (int j = 0; j < BN; j++) acc[j] = 0.f;
-        const int nsteps = nk * KSTEPS;
+        const int nsteps = (nk * KSTEPS + KS_PER_BUF - 1) / KS_PER_BUF;
         for (int g = 0; g < nsteps; g++) {
             const int buf = g % NBUF;
             mbar_wait(&accf[buf], (g / NBUF) & 1);
