@@ -522,8 +522,11 @@ __global__ void k_sum_chunks(const T* __restrict__ part, int nchunks, int np, T*
 // tensor of src/gpr/matern_kernel.rs:83-135 / product_kernel.rs:40-70):
 //   g_k = 1/2 sum_ij (alpha_i alpha_j - Kinv_ij) G_ijk,   k = noise, c, l_1..l_d   (lml.rs:61-71)
 // gpart[b][tile][0..p) receives this tile's contribution (symmetry: off-diagonal cells count twice).
+#ifndef HBEGP_GRAD_MINBLOCKS
+#define HBEGP_GRAD_MINBLOCKS 4  // 64 registers, 4 CTAs per SM: 6.8 -> 6.0 ms at the north-star shape (probes/grad_ab.py); the FP64 pipe bounds it
+#endif
 template <typename T, int NU2>
-__global__ void __launch_bounds__(256) k_grad_contract(const T* __restrict__ Kinv, long mstride, int n, int d,
+__global__ void __launch_bounds__(256, HBEGP_GRAD_MINBLOCKS) k_grad_contract(const T* __restrict__ Kinv, long mstride, int n, int d,
                                                        int np, const T* __restrict__ xsT,
                                                        const T* __restrict__ alpha, long astride,
                                                        const T* __restrict__ prm, int pstride,

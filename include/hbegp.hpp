@@ -9,6 +9,7 @@
 // It is the C++ twin of the `impl Estimator<A>` sketched in INTEGRATION.md and is what tests/cpp exercises.
 // Header-only; link with -lhbegp.  Panics of the reference are std::runtime_error here.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -210,7 +211,13 @@ std::vector<A> predict(const FittedKernel<A>& fk, const std::vector<A>& x, long 
     long below = 0;
     if (variance) variance->assign(m, A(0));
     check(hbegp_predict(fk.model->h, m, x.data(), mean.data(), variance ? variance->data() : nullptr, &below), "hbegp_predict");
-    if (below > 0) fprintf(stderr, "Variances below 0 were predicted and will be corrected: %ld value(s)\n", below);
+    if (below > 0) {  // predict.rs:39-46 lists the offending values ("{:.2e}", comma separated)
+        std::vector<double> vals((size_t)std::min<long>(below, 4096));
+        const int k = hbegp_predict_warn_values(fk.model->h, (int)vals.size(), vals.data(), nullptr);
+        fprintf(stderr, "Variances below 0 were predicted and will be corrected: ");
+        for (int i = 0; i < k; i++) fprintf(stderr, i ? ", %.2e" : "%.2e", vals[i]);
+        fprintf(stderr, "\n");
+    }
     return mean;
 }
 
