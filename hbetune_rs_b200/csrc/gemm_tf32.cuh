@@ -35,9 +35,17 @@
 namespace hbegp {
 namespace tf32 {
 
-constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
-constexpr int TILE_BYTES = BM * BK * 4;  // 16 KB: one operand tile (hi or lo)
+// Stage depth: 32 k per stage (128-byte rows, three 64 KB stages).  A finer ring -- 16 k per stage, six 32 KB stages, 64-byte
+// rows with SWIZZLE_64B -- was measured as well (compile with -DHBEGP_TF32_BK=16): 120-125 TFLOP/s against 132-137 on
+// 4096^3; the doubled number of barrier hand-shakes costs more than the shorter slot residence gains.
+#ifndef HBEGP_TF32_BK
+#define HBEGP_TF32_BK 32
+#endif
+constexpr int BM = 128, BN = 128, BK = HBEGP_TF32_BK, STAGES = 192 / (BK * 2);
+static_assert(BK == 16 || BK == 32, "BK: 16 (64-byte rows, SWIZZLE_64B) or 32 (128-byte rows, SWIZZLE_128B)");
+constexpr int TILE_BYTES = BM * BK * 4;  // one operand tile (hi or lo): 8 KB (BK = 16) or 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // A_hi, A_lo, B_hi, B_lo
+constexpr int MN_BOX_BYTES = 32 * BK * 4;    // one TMA box of a row-major operand: BK k-rows x 32 rows (128 bytes)
 constexpr int THREADS = 320;
 constexpr int NBUF = 3;         // TMEM buffers the hi*hi products of successive k steps rotate through
 #ifndef HBEGP_TF32_KS_PER_BUF
@@ -240,14 +248,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
                 } else {
 #pragma unroll
                     for (int j = 0; j < BM / 32; j++)  // four boxes (32 rows contiguous, 32 k)
-                        tma_load_3d(&p.mapA, &full[s], st + j * 4096, m0 + 32 * j, k0, bz);
+                        tma_load_3d(&p.mapA, &full[s], st + j * MN_BOX_BYTES, m0 + 32 * j, k0, bz);
                 }
                 unsigned char* sb = st + 2 * TILE_BYTES;
                 if (B_KMAJOR) {
                     tma_load_3d(&p.mapB, &full[s], sb, k0, n0, bz);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < BN / 32; j++) tma_load_3d(&p.mapB, &full[s], sb + j * 4096, n0 + 32 * j, k0, bz);
+                    for (int j = 0; j < BN / 32; j++) tma_load_3d(&p.mapB, &full[s], sb + j * MN_BOX_BYTES, n0 + 32 * j, k0, bz);
                 }
             }
         }
@@ -259,9 +267,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32x3_kernel(const __grid_co
             // inside the swizzled row.
             // MN-major (per 32-row box: 32 k-rows x 128 bytes of rows): 32-row groups 4096 bytes apart (LBO), groups of
             // 4 k-rows 512 bytes apart (SBO); one k step of 8 = 1024 bytes.
-            constexpr uint32_t a_lbo = A_KMAJOR ? 16 : 4096, a_sbo = A_KMAJOR ? 1024 : 512, a_kstep = A_KMAJOR ? 32 : 1024;
-            constexpr uint32_t b_lbo = B_KMAJOR ? 16 : 4096, b_sbo = B_KMAJOR ? 1024 : 512, b_kstep = B_KMAJOR ? 32 : 1024;
-            constexpr uint32_t a_lay = A_KMAJOR ? 2 : 1, b_lay = B_KMAJOR ? 2 : 1;
+            // (BK = 16: K-major rows are 64 bytes, SWIZZLE_64B, 8-row groups 512 bytes apart; MN-major boxes hold 16 k-rows,
+            // so the 32-row groups are 2048 bytes apart.)
+            constexpr uint32_t k_sbo = 8 * BK * 4, k_lay = (BK == 32) ? 2 : 4;  // SWIZZLE_128B / SWIZZLE_64B
+            constexpr uint32_t a_lbo = A_KMAJOR ? 16 : MN_BOX_BYTES, a_sbo = A_KMAJOR ? k_sbo : 512, a_kstep = A_KMAJOR ? 32 : 1024;
+            constexpr uint32_t b_lbo = B_KMAJOR ? 16 : MN_BOX_BYTES, b_sbo = B_KMAJOR ? k_sbo : 512, b_kstep = B_KMAJOR ? 32 : 1024;
+            constexpr uint32_t a_lay = A_KMAJOR ? k_lay : 1, b_lay = B_KMAJOR ? k_lay : 1;
             for (int kt = 0; kt < nk; kt++) {
                 const int s = kt % STAGES;
                 mbar_wait(&xf[s], (kt / STAGES) & 1);
@@ -417,16 +428,17 @@ inline EncodeTiledFn encode_fn() {
 }
 
 // Tensor map of one operand: `rows` x `kdim` elements of which the k-major flavour has k contiguous (X[r * ld + k]) and
-// the other has rows contiguous (X[k * ld + r]); third dimension = batch.  Boxes: (32 k, 128 rows) resp. (32 rows, 32 k).
+// the other has rows contiguous (X[k * ld + r]); third dimension = batch.  Boxes: (BK k, 128 rows) resp. (32 rows, BK k).
 inline bool make_operand_map(CUtensorMap* map, const float* base, bool kmajor, int rows, int kdim, long ld, long batch_stride, int batch) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return false;
     cuuint64_t dims[3] = {(cuuint64_t)(kmajor ? kdim : rows), (cuuint64_t)(kmajor ? rows : kdim), (cuuint64_t)batch};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(batch > 1 ? batch_stride : (long)dims[1] * ld) * 4};
-    cuuint32_t box[3] = {32, (cuuint32_t)(kmajor ? BM : 32), 1};
+    cuuint32_t box[3] = {(cuuint32_t)(kmajor ? BK : 32), (cuuint32_t)(kmajor ? BM : BK), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, kmajor ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     kmajor ? (BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B) : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
