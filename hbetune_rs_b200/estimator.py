@@ -155,7 +155,7 @@ class SurrogateModelGPR:
         m = x.shape[0]
         mean, ei = np.empty(m, dtype=self.A), np.empty(m, dtype=self.A)
         best, nb = C.c_long(-1), C.c_long(0)
-        check(lib.hbegp_predict_mean_ei(self.fitted.model._h, C.byref(self.y_norm._raw), m, _ptr(x), float(fmin), _ptr(mean),
+        check(lib.hbegp_predict_mean_ei(self.fitted.model.single_handle(), C.byref(self.y_norm._raw), m, _ptr(x), float(fmin), _ptr(mean),
                                         _ptr(ei), C.byref(best) if want_best else None, C.byref(nb)), "hbegp_predict_mean_ei")
         return mean, ei, best.value
 
@@ -166,7 +166,7 @@ class SurrogateModelGPR:
         m = x.shape[0]
         out = np.empty(m, dtype=self.A)
         best, nb = C.c_long(-1), C.c_long(0)
-        check(lib.hbegp_predict_confidence_bound(self.fitted.model._h, C.byref(self.y_norm._raw), m, _ptr(x), float(cb), _ptr(out),
+        check(lib.hbegp_predict_confidence_bound(self.fitted.model.single_handle(), C.byref(self.y_norm._raw), m, _ptr(x), float(cb), _ptr(out),
                                                  C.byref(best) if want_best else None, C.byref(nb)),
               "hbegp_predict_confidence_bound")
         return out, best.value

@@ -376,6 +376,9 @@ class Model:
                   + ", ".join(f"{v:.2e}" for v in vals) + more, file=sys.stderr)
         return mean, var
 
+    def single_handle(self):
+        return self._h
+
     def warn_values(self, cap: int = 16):
         """The pre-clamp variances below -sqrt(1e-5) of the last prediction, in row order, with their rows
         (``hbegp_predict_warn_values``; ``predict.rs:39-46``, ``:104-127``)."""
@@ -456,20 +459,25 @@ class MultiContext:
               "hbegp_multi_fit_runs")
         return res, best_theta
 
-    def model(self, theta, nu: float = 2.5, lo=None, hi=None) -> "MultiModel":
-        return MultiModel(self, theta, nu, lo, hi)
+    def model(self, theta, nu: float = 2.5, lo=None, hi=None, want_alpha=True, want_kinv=False) -> "MultiModel":
+        return MultiModel(self, theta, nu, lo, hi, want_alpha, want_kinv)
 
 
 class MultiModel:
     """``hbegp_multi_model``: one evaluation on GPU 0, replicas on the other GPUs over NVLink."""
 
-    def __init__(self, mctx: MultiContext, theta, nu=2.5, lo=None, hi=None):
-        self.mctx, self.A, self.d = mctx, mctx.A, mctx.d
+    def __init__(self, mctx: MultiContext, theta, nu=2.5, lo=None, hi=None, want_alpha=True, want_kinv=False):
+        self.mctx = self.ctx = mctx
+        self.A, self.n, self.d = mctx.A, mctx.n, mctx.d
+        self.appended = False
+        self.alpha = np.empty(mctx.n, dtype=self.A) if want_alpha else None
+        self.k_inv = np.empty((mctx.n, mctx.n), dtype=self.A) if want_kinv else None
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         lo = None if lo is None else np.ascontiguousarray(lo, dtype=np.float64)
         hi = None if hi is None else np.ascontiguousarray(hi, dtype=np.float64)
         h, lml = C.c_void_p(), C.c_double()
-        rc = lib.hbegp_multi_model_create(mctx._h, nu, _ptr(theta), _ptr(lo), _ptr(hi), C.byref(h), C.byref(lml), None, None)
+        rc = lib.hbegp_multi_model_create(mctx._h, nu, _ptr(theta), _ptr(lo), _ptr(hi), C.byref(h), C.byref(lml),
+                                          _ptr(self.alpha), _ptr(self.k_inv))
         if rc == _lib.NOT_PD:
             raise np.linalg.LinAlgError("Kernel matrix must be invertible.")
         check(rc, "hbegp_multi_model_create")
@@ -483,7 +491,11 @@ class MultiModel:
     def __del__(self):
         self.close()
 
-    def predict(self, xs, want_variance: bool = True):
+    def single_handle(self):
+        """GPU 0's replica as a plain ``hbegp_model`` (for the single-GPU acquisition epilogues)."""
+        return C.c_void_p(lib.hbegp_multi_model_replica(self._h, 0))
+
+    def predict(self, xs, want_variance: bool = True, warn: bool = True):
         xs = np.ascontiguousarray(xs, dtype=self.A)
         m = xs.shape[0]
         mean = np.empty(m, dtype=self.A)
@@ -491,6 +503,9 @@ class MultiModel:
         nb = C.c_long(0)
         check(lib.hbegp_multi_predict(self._h, m, _ptr(xs), _ptr(mean), _ptr(var), C.byref(nb)), "hbegp_multi_predict")
         self.n_below_warn = nb.value
+        if warn and nb.value:
+            print(f"Variances below 0 were predicted and will be corrected: {nb.value} value(s) over {self.mctx.n_gpus} GPUs",
+                  file=sys.stderr)
         return mean, var
 
 
