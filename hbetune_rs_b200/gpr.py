@@ -569,7 +569,7 @@ class FittedKernel:
         theta = np.array([math.log(noise.value)] + kernel.theta())
         try:
             pm = getattr(prior, "model", None)
-            if (pm is not None and getattr(pm, "_h", None) and pm.ctx is ctx
+            if (isinstance(pm, Model) and isinstance(ctx, Context) and getattr(pm, "_h", None) and pm.ctx is ctx
                     and prior.noise.value == noise.value and prior.kernel.theta() == kernel.theta()
                     and prior.kernel.k2.nu == kernel.k2.nu):
                 model = Model(ctx, want_alpha=True, want_kinv=want_kinv, prior=pm)
