@@ -349,8 +349,7 @@ struct Engine : EngineBase {
         const bool alloc_only = on_device && !x && !y;  // alloc_data(): buffers sized and padded, contents arrive by broadcast
         if (n_ <= 0 || d_ <= 0 || (!alloc_only && (!x || !y))) return fail(HBEGP_ERR_INVALID, "set_data: n, d must be positive and x, y non-null");
         if (n_ > 46000) return fail(HBEGP_ERR_INVALID, "set_data: n too large for a single-GPU factorisation");
-        if ((2 * (size_t)d_ * TILE + 2 * TILE) * sizeof(T) + 8 * (size_t)(d_ + 2) * sizeof(double) > kMaxFeatureSmem)
-            return fail(HBEGP_ERR_UNSUPPORTED, "set_data: too many features for the shared-memory tiles of the assembly kernels");
+        if (d_ > 65536) return fail(HBEGP_ERR_UNSUPPORTED, "set_data: more than 65536 features");
         CUDA_TRY(cudaSetDevice(device));
         const void *oldx = dX.p, *oldy = dY.p;
         const bool same_shape = (n == n_ && d == d_);
@@ -545,7 +544,7 @@ struct Engine : EngineBase {
         T* al = (T*)alpha.p + (size_t)s0 * np;
         T* tp = (T*)tpart.p + (size_t)s0 * nchunks() * np;
         double* gp = (double*)gpart.p + (size_t)s0 * ntiles_lower() * p();
-        const size_t xsm = 2 * (size_t)d * TILE * sizeof(T);
+        const size_t xsm = 2 * (size_t)feat_chunk(d) * TILE * sizeof(T);
         if (phase == 5) return lauum(st, Ab, Wb, cnt);  // benchmark only: the K^-1 product on the W of the last evaluation
         k_scale_x<T><<<dim3((np + 255) / 256, d, cnt), 256, 0, st>>>((const T*)dX.p, (int)n, d, np, pr, p(), xs);
         launches++;
@@ -568,7 +567,7 @@ struct Engine : EngineBase {
         }
         if (phase < 3) return HBEGP_OK;
         if (want_grad) {
-            const size_t gsm = xsm + 2 * TILE * sizeof(T) + 8 * (size_t)p() * sizeof(double);
+            const size_t gsm = xsm + 2 * TILE * sizeof(T) + 8 * (size_t)(feat_chunk(d) + 2) * sizeof(double);
             k_grad_contract<T, NU2><<<dim3(ntiles_lower(), 1, cnt), 256, gsm, st>>>(
                 Ab, mstride(), (int)n, d, np, xs, al, np, pr, p(), gp, (long)ntiles_lower() * p());
             launches++;
@@ -754,7 +753,6 @@ struct Engine : EngineBase {
     template <int NU2>
     int kernel_matrix_nu(int dd, const double* theta, long n1, const void* x1, long n2, const void* x2, void* out) {
         const int np2 = round_up(n2, TILE);
-        if ((2 * (size_t)dd * TILE + 2 * TILE) * sizeof(T) > kMaxFeatureSmem) return fail(HBEGP_ERR_UNSUPPORTED, "kernel_matrix: too many features");
         std::vector<T> prm_h(dd + 2);
         prm_h[0] = T(0);
         for (int k = 1; k < dd + 2; k++) prm_h[k] = (T)std::exp(theta[k - 1]);
@@ -778,7 +776,7 @@ struct Engine : EngineBase {
         if (ce != cudaSuccess) return done(fail(HBEGP_ERR_CUDA, std::string("kernel_matrix: ") + cudaGetErrorString(ce)));
         k_scale_x<T><<<dim3((np2 + 255) / 256, dd, 1), 256, 0, st>>>((const T*)dx2.p, (int)n2, dd, np2, (const T*)dprm.p, dd + 2, (T*)dxsT.p);
         launches++;
-        const size_t ksm = (2 * (size_t)dd * TILE + TILE) * sizeof(T);
+        const size_t ksm = (2 * (size_t)feat_chunk(dd) * TILE + TILE) * sizeof(T);
         for (long row0 = 0; row0 < n1; row0 += chunk) {
             const long rows = std::min(chunk, n1 - row0);
             const int rows_p = round_up(rows, TILE);
@@ -864,7 +862,7 @@ struct Engine : EngineBase {
         DevBuf tmp;
         if ((rc = tmp.ensure((size_t)n * n * sizeof(T)))) return rc;
         dim3 fg((unsigned)((n + 255) / 256), (unsigned)n);
-        const size_t xsm = 2 * (size_t)d * TILE * sizeof(T);
+        const size_t xsm = 2 * (size_t)feat_chunk(d) * TILE * sizeof(T);
         auto copy_out = [&](const T* src, void* dst, int mode) -> int {
             k_sym_fill<T><<<fg, 256, 0, stream>>>(src, np, (int)n, (T*)tmp.p, mode);
             CUDA_TRY(cudaMemcpyAsync(dst, tmp.p, (size_t)n * n * sizeof(T), cudaMemcpyDeviceToHost, stream));
@@ -931,7 +929,7 @@ struct ModelT : Model {
         Engine<T>* e = static_cast<Engine<T>*>(eng);
         cudaStream_t st = e->stream;
         if (m <= 64 && (size_t)m * d * sizeof(T) <= 40 * 1024) return predict_small<NU2>((int)m, xs, mean, var, nb);
-        const size_t ksm = (2 * (size_t)d * TILE + TILE) * sizeof(T);
+        const size_t ksm = (2 * (size_t)feat_chunk(d) * TILE + TILE) * sizeof(T);
         const int ttiles = np / TILE;
         // The train tiles are split over grid.y in FIXED groups of 16 (1024 training rows); the partial means are summed
         // in group order by k_var_finish.  A fixed group size (instead of one chosen from the number of candidate
@@ -1052,7 +1050,7 @@ struct ModelT : Model {
         if (ce == cudaSuccess) ce = cudaMemsetAsync(e->d_status.p, 0, sizeof(int), st);
         if (ce == cudaSuccess) {
             const int nt = (np / TILE) * (np / TILE + 1) / 2;
-            k_assemble<T, NU2><<<dim3(nt, 1, 1), 256, 2 * (size_t)this->d * TILE * sizeof(T), st>>>((const T*)xsT.p, (int)n, this->d, np, (const T*)tprm.p, p,
+            k_assemble<T, NU2><<<dim3(nt, 1, 1), 256, 2 * (size_t)feat_chunk(this->d) * TILE * sizeof(T), st>>>((const T*)xsT.p, (int)n, this->d, np, (const T*)tprm.p, p,
                                                                                                    (T*)e->A.p, (long)np * np, 0);
             e->launches++;
             ce = cudaGetLastError();
@@ -1353,7 +1351,7 @@ int Engine<T>::append_nu(ModelT<T>* prior, int r1, bool want_kinv) {
     T* xs = (T*)xsT.p;
     T* pr = (T*)prm.p;
     const int q = r1 / TILE, tile0 = q * (q + 1) / 2;
-    const size_t xsm = 2 * (size_t)d * TILE * sizeof(T);
+    const size_t xsm = 2 * (size_t)feat_chunk(d) * TILE * sizeof(T);
     if (ntiles_lower() > tile0) {
         k_assemble<T, NU2><<<dim3(ntiles_lower() - tile0, 1, 1), 256, xsm, st>>>(xs, (int)n, d, np, pr, p(), Ab, mstride(), tile0);
         launches++;

@@ -10,6 +10,11 @@
 namespace hbegp {
 
 constexpr int TILE = 64;  // leaf / tile edge
+// Feature chunk of the kernels that stage d x 64 operand tiles in shared memory (assembly, gradient contraction, k*):
+// up to this many features are staged at once, more are processed in chunks of this size (same left-to-right
+// accumulation order), so d is unbounded and the shared-memory footprint is not.
+constexpr int kFeatChunk = 64;
+__host__ __device__ inline int feat_chunk(int d) { return d < kFeatChunk ? d : kFeatChunk; }
 
 // `ulps_eq!(std, 0.0)` of expected_improvement (src/core/acquisition.rs:148): approx 0.3 tests abs_diff_eq with
 // epsilon = f64::EPSILON first, so any |std| <= 2.2e-16 takes the trivial branch (the ULP test that follows can only
@@ -109,19 +114,14 @@ __global__ void __launch_bounds__(256) k_assemble(const T* __restrict__ xsT, int
                                                   const T* __restrict__ prm, int pstride, T* __restrict__ K,
                                                   long kstride, int tile0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* xi = reinterpret_cast<T*>(smem_raw);  // [d][64]
-    T* xj = xi + d * TILE;
+    const int dc = feat_chunk(d);
+    T* xi = reinterpret_cast<T*>(smem_raw);  // [dc][64]
+    T* xj = xi + dc * TILE;
     int mt, nt;
     lower_tile(blockIdx.x + tile0, mt, nt);  // tile0 > 0: only the tile rows an append adds (model_extend)
     const int b = blockIdx.z;
     const int i0 = mt * TILE, j0 = nt * TILE;
     const T* xb = xsT + (long)b * d * np;
-    for (int e = threadIdx.x; e < d * TILE; e += 256) {
-        int k = e / TILE, r = e % TILE;
-        xi[e] = xb[(long)k * np + i0 + r];
-        xj[e] = xb[(long)k * np + j0 + r];
-    }
-    __syncthreads();
     const T noise = prm[(long)b * pstride + 0], c = prm[(long)b * pstride + 1];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     T acc[4][4];
@@ -129,19 +129,29 @@ __global__ void __launch_bounds__(256) k_assemble(const T* __restrict__ xsT, int
     for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int q = 0; q < 4; q++) acc[a][q] = T(0);
-    for (int k = 0; k < d; k++) {
-        T vi[4], vj[4];
+    for (int c0 = 0; c0 < d; c0 += dc) {
+        const int dl = min(dc, d - c0);
+        if (c0 > 0) __syncthreads();  // the previous chunk has been consumed
+        for (int e = threadIdx.x; e < dl * TILE; e += 256) {
+            int k = e / TILE, r = e % TILE;
+            xi[e] = xb[(long)(c0 + k) * np + i0 + r];
+            xj[e] = xb[(long)(c0 + k) * np + j0 + r];
+        }
+        __syncthreads();
+        for (int k = 0; k < dl; k++) {
+            T vi[4], vj[4];
 #pragma unroll
-        for (int a = 0; a < 4; a++) vi[a] = xi[k * TILE + ty + 16 * a];
+            for (int a = 0; a < 4; a++) vi[a] = xi[k * TILE + ty + 16 * a];
 #pragma unroll
-        for (int q = 0; q < 4; q++) vj[q] = xj[k * TILE + tx + 16 * q];
+            for (int q = 0; q < 4; q++) vj[q] = xj[k * TILE + tx + 16 * q];
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+            for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                T df = vi[a] - vj[q];
-                acc[a][q] += df * df;
-            }
+                for (int q = 0; q < 4; q++) {
+                    T df = vi[a] - vj[q];
+                    acc[a][q] += df * df;
+                }
+        }
     }
     T* Kb = K + (long)b * kstride;
 #pragma unroll
@@ -532,22 +542,25 @@ __global__ void __launch_bounds__(256, HBEGP_GRAD_MINBLOCKS) k_grad_contract(con
                                                        const T* __restrict__ prm, int pstride,
                                                        double* __restrict__ gpart, long gp_bstride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* xi = reinterpret_cast<T*>(smem_raw);  // [d][64]
-    T* xj = xi + d * TILE;                   // [d][64]
-    T* ai = xj + d * TILE;                   // [64]
+    const int dc = feat_chunk(d);
+    T* xi = reinterpret_cast<T*>(smem_raw);  // [dc][64]
+    T* xj = xi + dc * TILE;                  // [dc][64]
+    T* ai = xj + dc * TILE;                  // [64]
     T* aj = ai + TILE;                       // [64]
-    double* wsum = reinterpret_cast<double*>(aj + TILE);  // [8][p]
-    const int p = d + 2;
+    double* wsum = reinterpret_cast<double*>(aj + TILE);  // [8][dc + 2]: per-warp partials of one feature chunk (+ noise, c)
+    const int p = d + 2, ws = dc + 2;
     int mt, nt;
     lower_tile(blockIdx.x, mt, nt);
     const int b = blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i0 = mt * TILE, j0 = nt * TILE;
     const T* xb = xsT + (long)b * d * np;
-    for (int e = tid; e < d * TILE; e += 256) {
-        int k = e / TILE, r = e % TILE;
-        xi[e] = xb[(long)k * np + i0 + r];
-        xj[e] = xb[(long)k * np + j0 + r];
-    }
+    auto load_chunk = [&](int c0, int dl) {
+        for (int e = tid; e < dl * TILE; e += 256) {
+            int k = e / TILE, r = e % TILE;
+            xi[e] = xb[(long)(c0 + k) * np + i0 + r];
+            xj[e] = xb[(long)(c0 + k) * np + j0 + r];
+        }
+    };
     if (tid < TILE) ai[tid] = alpha[(long)b * astride + i0 + tid];
     else if (tid < 2 * TILE) aj[tid - TILE] = alpha[(long)b * astride + j0 + tid - TILE];
     const int tx = tid & 15, ty = tid >> 4;
@@ -559,7 +572,6 @@ __global__ void __launch_bounds__(256, HBEGP_GRAD_MINBLOCKS) k_grad_contract(con
     for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int q = 0; q < 4; q++) kv[a * 4 + q] = Kb[(long)(i0 + ty + 16 * a) * np + j0 + tx + 16 * q];
-    __syncthreads();
     const T noise = prm[(long)b * pstride + 0], c = prm[(long)b * pstride + 1];
     T cm[16];
     double g_noise = 0.0, g_c = 0.0;
@@ -567,19 +579,25 @@ __global__ void __launch_bounds__(256, HBEGP_GRAD_MINBLOCKS) k_grad_contract(con
         T S[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) S[e] = T(0);
-        for (int k = 0; k < d; k++) {
-            T vi[4], vj[4];
+        for (int c0 = 0; c0 < d; c0 += dc) {  // squared scaled distances, feature chunk by feature chunk
+            const int dl = min(dc, d - c0);
+            if (c0 > 0) __syncthreads();
+            load_chunk(c0, dl);
+            __syncthreads();
+            for (int k = 0; k < dl; k++) {
+                T vi[4], vj[4];
 #pragma unroll
-            for (int a = 0; a < 4; a++) vi[a] = xi[k * TILE + ty + 16 * a];
+                for (int a = 0; a < 4; a++) vi[a] = xi[k * TILE + ty + 16 * a];
 #pragma unroll
-            for (int q = 0; q < 4; q++) vj[q] = xj[k * TILE + tx + 16 * q];
+                for (int q = 0; q < 4; q++) vj[q] = xj[k * TILE + tx + 16 * q];
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+                for (int a = 0; a < 4; a++)
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    T df = vi[a] - vj[q];
-                    S[a * 4 + q] += df * df;
-                }
+                    for (int q = 0; q < 4; q++) {
+                        T df = vi[a] - vj[q];
+                        S[a * 4 + q] += df * df;
+                    }
+            }
         }
 #pragma unroll
         for (int a = 0; a < 4; a++)
@@ -609,32 +627,48 @@ __global__ void __launch_bounds__(256, HBEGP_GRAD_MINBLOCKS) k_grad_contract(con
     g_noise = warp_sum(g_noise);
     g_c = warp_sum(g_c);
     if (lane == 0) {
-        wsum[warp * p + 0] = g_noise;
-        wsum[warp * p + 1] = g_c;
+        wsum[warp * ws + dc] = g_noise;
+        wsum[warp * ws + dc + 1] = g_c;
     }
-    for (int k = 0; k < d; k++) {
-        T vi[4], vj[4];
+    double* gout = gpart + (long)b * gp_bstride + (long)blockIdx.x * p;
+    for (int c0 = 0; c0 < d; c0 += dc) {
+        const int dl = min(dc, d - c0);
+        if (d > dc) {  // more than one chunk: the tiles of chunk c0 have to come back (a single chunk is still there)
+            __syncthreads();
+            load_chunk(c0, dl);
+            __syncthreads();
+        }
+        for (int k = 0; k < dl; k++) {
+            T vi[4], vj[4];
 #pragma unroll
-        for (int a = 0; a < 4; a++) vi[a] = xi[k * TILE + ty + 16 * a];
+            for (int a = 0; a < 4; a++) vi[a] = xi[k * TILE + ty + 16 * a];
 #pragma unroll
-        for (int q = 0; q < 4; q++) vj[q] = xj[k * TILE + tx + 16 * q];
-        T acc = T(0);
+            for (int q = 0; q < 4; q++) vj[q] = xj[k * TILE + tx + 16 * q];
+            T acc = T(0);
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+            for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                T df = vi[a] - vj[q];
-                acc += cm[a * 4 + q] * (df * df);
-            }
-        double v = warp_sum((double)acc);
-        if (lane == 0) wsum[warp * p + 2 + k] = v;
-    }
-    __syncthreads();
-    if (tid < p) {
-        double s = 0.0;
+                for (int q = 0; q < 4; q++) {
+                    T df = vi[a] - vj[q];
+                    acc += cm[a * 4 + q] * (df * df);
+                }
+            double v = warp_sum((double)acc);
+            if (lane == 0) wsum[warp * ws + k] = v;
+        }
+        __syncthreads();
+        if (tid < dl) {
+            double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < 8; w++) s += wsum[w * p + tid];
-        gpart[(long)b * gp_bstride + (long)blockIdx.x * p + tid] = 0.5 * s;
+            for (int w = 0; w < 8; w++) s += wsum[w * ws + tid];
+            gout[2 + c0 + tid] = 0.5 * s;
+        }
+        if (c0 == 0 && tid >= 64 && tid < 66) {  // noise and amplitude components, once
+            const int which = tid - 64;
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) s += wsum[w * ws + dc + which];
+            gout[which] = 0.5 * s;
+        }
     }
 }
 
@@ -702,44 +736,52 @@ __global__ void __launch_bounds__(256) k_kstar_mean(const T* __restrict__ xs, lo
     // grid.y splits the train tiles when there are too few candidate tiles to fill the GPU; the partial means of
     // split y go to pmean[y * pm_stride + chunk_row] and are summed in order by k_var_finish.
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* xc = reinterpret_cast<T*>(smem_raw);  // [d][64] candidates (scaled)
-    T* xt = xc + d * TILE;                   // [d][64] train tile
-    T* al = xt + d * TILE;                   // [64]
+    const int dc = feat_chunk(d);
+    T* xc = reinterpret_cast<T*>(smem_raw);  // [dc][64] candidates (scaled)
+    T* xt = xc + dc * TILE;                  // [dc][64] train tile
+    T* al = xt + dc * TILE;                  // [64]
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const long r0 = (long)blockIdx.x * TILE;  // row within the chunk
-    for (int e = tid; e < d * TILE; e += 256) {
-        int r = e / d, k = e % d;  // coalesced read of the row-major candidates
-        long gr = row0 + r0 + r;
-        xc[k * TILE + r] = (gr < m) ? xs[gr * d + k] / ls[k] : T(0);
-    }
+    auto load_candidates = [&](int c0, int dl) {
+        for (int e = tid; e < dl * TILE; e += 256) {
+            int r = e / dl, k = e % dl;  // (nearly) coalesced read of the row-major candidates
+            long gr = row0 + r0 + r;
+            xc[k * TILE + r] = (gr < m) ? xs[gr * d + c0 + k] / ls[c0 + k] : T(0);
+        }
+    };
+    if (d <= dc) load_candidates(0, d);  // one chunk: the candidate tile stays for all train tiles
     T macc[4] = {T(0), T(0), T(0), T(0)};
     const int jbeg = blockIdx.y * tiles_per_cta * TILE, jend = min(np, jbeg + tiles_per_cta * TILE);
     for (int j0 = jbeg; j0 < jend; j0 += TILE) {
-        __syncthreads();
-        for (int e = tid; e < d * TILE; e += 256) {
-            int k = e / TILE, r = e % TILE;
-            xt[e] = xsT_train[(long)k * np + j0 + r];
-        }
-        if (tid < TILE) al[tid] = alpha[j0 + tid];
-        __syncthreads();
         T acc[4][4];
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
             for (int q = 0; q < 4; q++) acc[a][q] = T(0);
-        for (int k = 0; k < d; k++) {
-            T vi[4], vj[4];
+        for (int c0 = 0; c0 < d; c0 += dc) {
+            const int dl = min(dc, d - c0);
+            __syncthreads();
+            for (int e = tid; e < dl * TILE; e += 256) {
+                int k = e / TILE, r = e % TILE;
+                xt[e] = xsT_train[(long)(c0 + k) * np + j0 + r];
+            }
+            if (d > dc) load_candidates(c0, dl);
+            if (c0 == 0 && tid < TILE) al[tid] = alpha[j0 + tid];
+            __syncthreads();
+            for (int k = 0; k < dl; k++) {
+                T vi[4], vj[4];
 #pragma unroll
-            for (int a = 0; a < 4; a++) vi[a] = xc[k * TILE + ty + 16 * a];
+                for (int a = 0; a < 4; a++) vi[a] = xc[k * TILE + ty + 16 * a];
 #pragma unroll
-            for (int q = 0; q < 4; q++) vj[q] = xt[k * TILE + tx + 16 * q];
+                for (int q = 0; q < 4; q++) vj[q] = xt[k * TILE + tx + 16 * q];
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+                for (int a = 0; a < 4; a++)
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    T df = vi[a] - vj[q];
-                    acc[a][q] += df * df;
-                }
+                    for (int q = 0; q < 4; q++) {
+                        T df = vi[a] - vj[q];
+                        acc[a][q] += df * df;
+                    }
+            }
         }
 #pragma unroll
         for (int a = 0; a < 4; a++)

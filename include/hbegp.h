@@ -65,9 +65,9 @@ long long hbegp_ctx_launch_count(hbegp_ctx* ctx);
 
 /* Training data of the current fit: X (n x d), y (n).  Replaces the x_train / y_train arguments of
  * LmlWithGradient::of (src/gpr/lml.rs:16-27) and FittedKernel::new (src/gpr/fit.rs:18-31).
- * Limits of this implementation (the reference has none beyond host memory): n <= 46000 (one n x n factor and its
- * inverse per evaluation on one GPU) -> HBEGP_ERR_INVALID; d <= 195 in f64 / 390 in f32 (two d x 64 operand tiles
- * of the assembly kernels live in shared memory) -> HBEGP_ERR_UNSUPPORTED. */
+ * Limit of this implementation (the reference has none beyond host memory): n <= 46000 (one n x n factor and its inverse
+ * per evaluation must fit one GPU) -> HBEGP_ERR_INVALID.  The feature count is not limited in practice (<= 65536): the
+ * kernels stage features in chunks of 64. */
 int hbegp_set_data(hbegp_ctx* ctx, long n, int d, const void* x, const void* y);
 int hbegp_set_data_device(hbegp_ctx* ctx, long n, int d, const void* x_device, const void* y_device);
 

@@ -220,7 +220,9 @@ def test_size_limits_are_reported():
     from hbetune_rs_b200._lib import HbegpError
     ctx = _ctx()
     with pytest.raises(HbegpError):
-        ctx.set_data(np.zeros((10, 300)), np.zeros(10))  # more features than the shared-memory tiles hold
+        ctx.set_data(np.zeros((2, 70000)), np.zeros(2))  # the only cap on the feature count (chunks of 64 handle the rest)
+    with pytest.raises(HbegpError):
+        ctx.set_data(np.zeros((0, 3)), np.zeros(0))  # no rows
     x, y = synth(50, 2)
     ctx.set_data(x, y)  # the context stays usable
     assert np.isfinite(ctx.lml_grad_batch(_theta(2)[None, :])[0][0])

@@ -80,9 +80,6 @@ def test_unsupported_nu_and_errors():
     x, y = synth(10, 2)
     with _ctx(np.float64) as ctx:
         with pytest.raises(h.HbegpError) as e:
-            ctx.set_data(np.zeros((4, 400)), np.zeros(4))  # feature tiles would not fit shared memory
-        assert e.value.code == -4
-        with pytest.raises(h.HbegpError) as e:
             ctx.lml_grad_batch(random_thetas(1, 0))  # no data yet
         ctx.set_data(x, y)
         with pytest.raises(h.HbegpError) as e:
@@ -290,3 +287,34 @@ def test_large_gemm_tile_reads_no_stale_workspace(monkeypatch):
             assert abs(res[tile][0][b] - ref.lml) <= 1e-9 * abs(ref.lml)
             g_ref = np.array(ref.lml_gradient)
             np.testing.assert_allclose(res[tile][1][b], g_ref, rtol=1e-8, atol=1e-9 * np.abs(g_ref).max())
+
+
+@pytest.mark.parametrize("A,d", [(np.float64, 200), (np.float64, 65), (np.float32, 300)])
+def test_many_features_are_processed_in_chunks(A, d):
+    """The d x 64 operand tiles of the assembly / gradient / k* kernels are staged 64 features at a time, so d is not
+    limited by shared memory (round 1 refused d > 195).  LML, every gradient component, mean and variance against the oracle."""
+    n, m = 150, 130
+    x, y = synth(n, d, A=A)
+    rng = np.random.default_rng(9)
+    theta = np.concatenate([[math.log(0.1), math.log(1.3)], rng.uniform(math.log(2.0), math.log(9.0), d)])
+    xs = rng.random((m, d)).astype(A)
+    ref = oracle_lml(theta, x, y, A=A)
+    var_ref = np.zeros(m, dtype=A)
+    mean_ref = ogpr.predict(oracle_kernel(theta), ref.alpha, xs, x, ref.factorization.invc(), var_ref, A)
+    with _ctx(A) as ctx:
+        ctx.set_data(x, y)
+        lml, grad, status = ctx.lml_grad_batch(np.stack([theta, theta]))
+        model = ctx.model(theta)
+        mean, var = model.predict(xs)
+        mean1, var1 = model.predict(xs[:3])  # latency path
+        model.close()
+    tol = TOL[A]
+    assert status[0] == 0 and abs(lml[0] - ref.lml) <= tol * abs(ref.lml)
+    g_ref = np.array(ref.lml_gradient)
+    assert grad.shape == (2, d + 2) and (grad[0] == grad[1]).all()
+    np.testing.assert_allclose(grad[0], g_ref, rtol=tol * 10, atol=tol * np.abs(g_ref).max())
+    c = math.exp(theta[1])
+    np.testing.assert_allclose(mean, mean_ref, rtol=0, atol=tol * max(1.0, np.abs(mean_ref).max()))
+    np.testing.assert_allclose(var, var_ref, rtol=0, atol=tol * (c + 1e-5))
+    np.testing.assert_allclose(mean1, mean_ref[:3], rtol=0, atol=tol * max(1.0, np.abs(mean_ref).max()))
+    np.testing.assert_allclose(var1, var_ref[:3], rtol=0, atol=tol * (c + 1e-5))
