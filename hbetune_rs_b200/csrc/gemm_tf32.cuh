@@ -149,11 +149,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "r"(taddr));
 }
 
-__device__ __forceinline__ float rn_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+// Round to TF32 (11 significand bits), nearest with ties away from zero -- what cvt.rna.tf32.f32 does -- as two integer
+// operations.  nvcc expands cvt.rna.tf32.f32 into ~7 instructions on sm_100a (shift / add / mask plus Inf-NaN
+// special-casing, see the SASS), and with 128 elements per thread and k-block the four transform warps were ISSUE
+// BOUND on them: ncu put 47 % of the ALU pipe and the top stall samples of the whole kernel there while the tensor
+// pipe idled at 33 %.  Finite inputs only (a value within 2^-11 of FLT_MAX would round to Inf; the GP matrices are
+// nowhere near).
+__device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 // tile coordinates, heavy tiles first (same orders as gemm_kernel)
 __device__ __forceinline__ void tile_coords(const Params& p, int t, int tiles_m, int tiles_n, int& mt, int& nt) {
