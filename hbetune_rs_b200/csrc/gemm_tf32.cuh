@@ -35,6 +35,10 @@
 namespace hbegp {
 namespace tf32 {
 
+// What bounds the main loop now is shared-memory bandwidth: per 32-k block TMA writes 32 KB, the transform reads 32 KB and
+// writes 64 KB, and the twelve MMAs read 96 KB of operands -- 224 KB at 128 B/cycle = 1750 cycles against ~2000 measured
+// (the tensor pipe itself needs 1250).  Measured and rejected on the way: eight transform warps (145 vs 151 TFLOP/s), eight
+// drain warps (107 vs 113 at the time), descriptors hoisted out of the issue loop (no change).
 // Stage depth: 32 k per stage (128-byte rows, three 64 KB stages).  A finer ring -- 16 k per stage, six 32 KB stages, 64-byte
 // rows with SWIZZLE_64B -- was measured as well (compile with -DHBEGP_TF32_BK=16): 120-125 TFLOP/s against 132-137 on
 // 4096^3; the doubled number of barrier hand-shakes costs more than the shorter slot residence gains.
