@@ -56,6 +56,30 @@ def test_minimize_by_gradient_rosenbrock_in_box():
     assert abs(x[0] - 0.5) < 1e-6 and abs(x[1] - 0.25) < 1e-5
 
 
+def test_lbfgs_tolerances_are_settable():
+    """hbegp_lbfgs_set_tolerances: the stall / gradient stops stand in for NLopt's internal ones; switched off, maxeval is
+    the only stop like the reference's configuration (gradmin.rs:52-54)."""
+    from hbetune_rs_b200 import _lib
+    counts = {}
+
+    def quad(x):
+        counts["n"] = counts.get("n", 0) + 1
+        return float(((x - 0.3) ** 2).sum()), 2 * (x - 0.3)
+
+    try:
+        minimize = lib_minimizer(maxeval=60)
+        counts.clear()
+        x, f = minimize(quad, [1.5, -1.0, 0.7], [(-2.0, 2.0)] * 3)
+        with_tol = counts["n"]
+        assert f < 1e-12 and with_tol < 30  # converged and stopped on its own
+        assert _lib.lib.hbegp_lbfgs_set_tolerances(0.0, 0.0) == 0
+        counts.clear()
+        x2, f2 = minimize(quad, [1.5, -1.0, 0.7], [(-2.0, 2.0)] * 3)
+        assert f2 <= f and counts["n"] >= with_tol  # keeps going until it cannot move or maxeval
+    finally:
+        _lib.lib.hbegp_lbfgs_set_tolerances(1e-11, 1e-8)
+
+
 def test_minimize_handles_infinite_objective():
     minimize = lib_minimizer()
 
