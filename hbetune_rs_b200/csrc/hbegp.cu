@@ -1336,6 +1336,7 @@ Model* Engine<T>::new_empty_model(int nu2, const std::vector<double>& prm_host, 
         return nullptr;
     }
     models.push_back(m);
+    evict_old_models();  // replicas follow the same retained-model policy as locally built models
     return m;
 }
 
