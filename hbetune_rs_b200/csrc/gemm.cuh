@@ -15,6 +15,8 @@
 #include <stdint.h>
 #include <type_traits>
 
+#include "launch.h"
+
 // k depth of one pipeline stage and number of stages (probes/gemm_bench.cu: 16 x 3 and 32 x 2 are within 0.5 %)
 #ifndef HBEGP_BK
 #define HBEGP_BK 16
@@ -391,8 +393,7 @@ inline cudaError_t launch_gemm_cfg(const GemmArgs<T>& a, int batch, cudaStream_t
     long tiles = a.lower_only ? tm * (tm + 1) / 2 : tm * tn;
     if (tiles <= 0 || batch <= 0) return cudaSuccess;
     dim3 grid((unsigned)tiles, 1, (unsigned)batch);
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a);
-    return cudaGetLastError();
+    return launch_prio(kern, grid, dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, a);
 }
 
 // CTA tile choice.  Measured on B200 (probes/gemm_bench.cu, profiles/r01_gemm_tile_probe.log): the 64x64 tile

@@ -473,8 +473,7 @@ inline cudaError_t launch(const GemmArgs<float>& a, int batch, cudaStream_t stre
     const long tm = (a.M + BM - 1) / BM, tn = (a.N + BN - 1) / BN;
     const long tiles = a.lower_only ? tm * (tm + 1) / 2 : tm * tn;
     dim3 grid((unsigned)tiles, 1, (unsigned)batch);
-    gemm_tf32x3_kernel<AK, BKM><<<grid, THREADS, SMEM_BYTES, stream>>>(p);
-    return cudaGetLastError();
+    return launch_prio(gemm_tf32x3_kernel<AK, BKM>, grid, dim3(THREADS), SMEM_BYTES, stream, p);
 }
 
 // Policy (process-wide, set by hbegp_ctx_create from HBEGP_TF32 / HBEGP_TF32_MIN): whether f32 contractions go through

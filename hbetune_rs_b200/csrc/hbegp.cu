@@ -451,17 +451,15 @@ struct Engine : EngineBase {
         T* Ab = (T*)A.p + (size_t)s0 * mstride();
         T* Wb = (T*)W.p + (size_t)s0 * mstride();
         if (s == TILE) {
-            k_leaf<T><<<dim3(1, 1, cnt), 256, leaf_smem_bytes<T>(), st>>>(Ab, Wb, mstride(), np, r0, (T*)ldp.p + (size_t)s0 * (np / TILE), np / TILE,
-                                                       (int*)d_status.p + s0);
+            CUDA_TRY(launch_prio(k_leaf<T>, dim3(1, 1, cnt), dim3(256), leaf_smem_bytes<T>(), st, Ab, Wb, mstride(), np, r0,
+                                 (T*)ldp.p + (size_t)s0 * (np / TILE), np / TILE, (int*)d_status.p + s0));
             launches++;
-            CUDA_TRY(cudaGetLastError());
             return HBEGP_OK;
         }
         if (s == 2 * TILE && use_node128) {  // the bottom node of the tree in one launch
-            k_node128<T><<<dim3(1, 1, cnt), 256, node128_smem_bytes<T>(), st>>>(Ab, Wb, mstride(), np, r0, (T*)ldp.p + (size_t)s0 * (np / TILE),
-                                                                              np / TILE, (int*)d_status.p + s0);
+            CUDA_TRY(launch_prio(k_node128<T>, dim3(1, 1, cnt), dim3(256), node128_smem_bytes<T>(), st, Ab, Wb, mstride(), np, r0,
+                                 (T*)ldp.p + (size_t)s0 * (np / TILE), np / TILE, (int*)d_status.p + s0));
             launches++;
-            CUDA_TRY(cudaGetLastError());
             return HBEGP_OK;
         }
         int q = s / TILE, q1 = (q + 1) / 2;
@@ -560,7 +558,7 @@ struct Engine : EngineBase {
         launches++;
         k_trmv_lower_t_part<T><<<dim3(np / TILE, nchunks(), cnt), 256, 0, st>>>(Wb, mstride(), np, ub, np, tp, nchunks());
         launches++;
-        k_sum_chunks<T><<<dim3((np + 255) / 256, 1, cnt), 256, 0, st>>>(tp, nchunks(), np, al, np);
+        CUDA_TRY(launch_prio(k_sum_chunks<T>, dim3((np + 255) / 256, 1, cnt), dim3(256), 0, st, tp, nchunks(), np, al, (long)np));
         launches++;
         if (want_grad || want_kinv) {
             if ((rc = lauum(st, Ab, Wb, cnt))) return rc;
@@ -572,11 +570,10 @@ struct Engine : EngineBase {
                 Ab, mstride(), (int)n, d, np, xs, al, np, pr, p(), gp, (long)ntiles_lower() * p());
             launches++;
         }
-        k_finish<T><<<cnt, 256, 0, st>>>((const T*)dY.p, al, np, (int)n, np, (T*)ldp.p + (size_t)s0 * (np / TILE), np / TILE, gp,
-                                        (long)ntiles_lower() * p(), ntiles_lower(), p(), (int*)d_status.p + s0,
-                                        (double*)d_lml.p + s0, (double*)d_grad.p + (size_t)s0 * p(), want_grad ? 1 : 0);
+        CUDA_TRY(launch_prio(k_finish<T>, dim3(cnt), dim3(256), 0, st, (const T*)dY.p, al, np, (int)n, np, (T*)ldp.p + (size_t)s0 * (np / TILE),
+                             np / TILE, gp, (long)ntiles_lower() * p(), ntiles_lower(), p(), (int*)d_status.p + s0, (double*)d_lml.p + s0,
+                             (double*)d_grad.p + (size_t)s0 * p(), want_grad ? 1 : 0));
         launches++;
-        CUDA_TRY(cudaGetLastError());
         return HBEGP_OK;
     }
 
@@ -663,7 +660,8 @@ struct Engine : EngineBase {
             }
             if (ce != cudaSuccess) return fail(HBEGP_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
             CachedGraph cg;
-            ce = cudaGraphInstantiate(&cg.exec, graph, 0);
+            // per-node priorities (launch.h) only count in a graph instantiated with this flag
+            ce = cudaGraphInstantiate(&cg.exec, graph, LaunchPriority::get().small_ctas > 0 ? cudaGraphInstantiateFlagUseNodePriority : 0);
             cudaGraphDestroy(graph);
             if (ce != cudaSuccess) return fail(HBEGP_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
             cg.kernels = kernels;
