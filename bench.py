@@ -474,9 +474,11 @@ def main():
             "achieved": tf_kinv, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf_kinv / peak_tf,
             "traffic": kt.get("traffic") if args.dtype == "f64" and n == 4096 else None,
             "algorithmic_bytes": kt.get("algorithmic_bytes") if args.dtype == "f64" and n == 4096 else None,
-            "traffic_note": f"DRAM bytes of one ncu --set full launch over {kt.get('matrices', '?')} matrices "
-                            "(profiles/r01_kinv_gemm_early_ncu_raw.csv); algorithmic = 8 n (n + 1) bytes per matrix "
-                            "(W lower read once, K^-1 lower written once)",
+            "traffic_note": (f"DRAM bytes of one ncu --set full launch over {kt.get('matrices', '?')} matrices "
+                             "(profiles/r01_kinv_gemm_early_ncu_raw.csv); algorithmic = 8 n (n + 1) bytes per matrix "
+                             "(W lower read once, K^-1 lower written once)" if args.dtype == "f64" and n == 4096 else
+                             "no ncu DRAM capture of this launch; the f32 kernel's capture is at n = 2048 over 17 matrices "
+                             "(profiles/r02_tf32_gemm_ncu_raw.csv): 566 MB moved against 4 n (n + 1) x 17 = 285 MB algorithmic"),
             "launch_ms": phases["kinv_gemm_ms"], "matrices": nb,
             "peak_source": ("cuBLAS DGEMM 8192^3 (torch.matmul f64) measured in this run; MEASURED_PEAKS.json has no FP64 entry"
                             if args.dtype == "f64" else
