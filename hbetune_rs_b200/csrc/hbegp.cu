@@ -28,6 +28,7 @@
 #include "gemm.cuh"
 #include "gemm_tf32.cuh"
 #include "kernels.cuh"
+#include "node_mma.cuh"
 #include "lbfgs.h"
 #include "adapter.h"
 #include "comm.h"
@@ -147,6 +148,7 @@ struct EngineBase {
     bool use_side = true;
     int side_max_cnt = 4;  // also use the side stream at n > 2048 for groups of at most this many matrices
     bool use_node128 = true;
+    int node_v = 2;  // f64 bottom node: 2 = k_node128_v2 (register-resident panels + DMMA products), 1 = k_node128
     cudaEvent_t fork_ev = nullptr;
     long n = 0;
     int d = 0, np = 0;
@@ -457,6 +459,14 @@ struct Engine : EngineBase {
             return HBEGP_OK;
         }
         if (s == 2 * TILE && use_node128) {  // the bottom node of the tree in one launch
+            if constexpr (std::is_same<T, double>::value) {
+                if (node_v == 2) {
+                    CUDA_TRY(launch_prio(k_node128_v2<false>, dim3(1, 1, cnt), dim3(256), node128_v2_smem_bytes(), st, Ab, Wb, mstride(), np, r0,
+                                         (T*)ldp.p + (size_t)s0 * (np / TILE), np / TILE, (int*)d_status.p + s0, (long long*)nullptr));
+                    launches++;
+                    return HBEGP_OK;
+                }
+            }
             CUDA_TRY(launch_prio(k_node128<T>, dim3(1, 1, cnt), dim3(256), node128_smem_bytes<T>(), st, Ab, Wb, mstride(), np, r0,
                                  (T*)ldp.p + (size_t)s0 * (np / TILE), np / TILE, (int*)d_status.p + s0));
             launches++;
@@ -1454,6 +1464,8 @@ static int configure_gemms() {
     const int big = (int)kMaxFeatureSmem;
     CUDA_TRY(cudaFuncSetAttribute(k_leaf<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem_bytes<T>()));
     CUDA_TRY(cudaFuncSetAttribute(k_node128<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)node128_smem_bytes<T>()));
+    if constexpr (std::is_same<T, double>::value)
+        CUDA_TRY(cudaFuncSetAttribute(k_node128_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)node128_v2_smem_bytes()));
     CUDA_TRY(cudaFuncSetAttribute(k_assemble<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(k_assemble<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(k_assemble<T, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -1810,6 +1822,7 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
     }
     if (const char* s = getenv("HBEGP_SIDE")) e->use_side = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_NODE128")) e->use_node128 = atoi(s) != 0;
+    if (const char* s = getenv("HBEGP_NODE_V")) e->node_v = atoi(s);
     if (const char* s = getenv("HBEGP_SIDE_CNT")) e->side_max_cnt = atoi(s);
     if (const char* s = getenv("HBEGP_PAD")) {
         const bool pad = atoi(s) != 0;

@@ -317,6 +317,143 @@ __device__ __forceinline__ void leaf_core(T (*as)[TILE + 1], T (*ws)[TILE + 1], 
     __syncthreads();
 }
 
+// Second-generation leaf (round 2): same contract as leaf_core, far fewer barriers.
+//
+// leaf_core pays one CTA barrier + a shared-memory round trip per pivot (64 of them, ~250 ns each) and another 15 for
+// the diagonal-block inverses.  Here the panel is 8 wide and its pivot chain runs entirely in registers: every row
+// thread holds the 8x8 diagonal block (36 values, broadcast loads) and factors it redundantly — all threads compute
+// the same bits, nobody waits for anybody — while carrying its own row of the panel through the same eliminations.
+// One barrier pair per panel (8 panels) instead of one barrier per pivot.  The inverse is recursive doubling:
+// the eight 8x8 diagonal blocks are inverted column-per-thread in registers, then 16-, 32- and 64-wide blocks follow
+// from W21 = -W22 (L21 W11), two small products per level.
+template <typename T, int DBG>
+__device__ __forceinline__ void leaf_core_nb8(T (*as)[TILE + 1], T (*ws)[TILE + 1], T* rdv, T* dinv, int* fail, int tid) {
+    constexpr int NB = 8;
+    const int tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) ws[ty + 16 * a][tx + 16 * q] = T(0);
+    // ---- Cholesky on unscaled columns u_ij = L_ij L_jj, panels of 8
+    if (!(DBG & 1)) {
+        for (int P = 0; P < TILE / NB; P++) {
+            const int c0 = NB * P;
+            __syncthreads();
+            if (tid >= c0 && tid < TILE) {
+                const int i = tid;
+                T U[NB][NB], x[NB], rd[NB];
+#pragma unroll
+                for (int r = 0; r < NB; r++)
+#pragma unroll
+                    for (int k = 0; k <= r; k++) U[r][k] = as[c0 + r][c0 + k];
+#pragma unroll
+                for (int k = 0; k < NB; k++) x[k] = as[i][c0 + k];
+                bool bad = false;
+#pragma unroll
+                for (int j = 0; j < NB; j++) {
+                    T dj = U[j][j];
+                    if (!(dj > T(0)) || !(dj <= T(1e300))) {
+                        bad = true;
+                        dj = T(1);
+                    }
+                    rd[j] = pivot_rcp<T>(dj);
+                    const T lx = x[j] * rd[j];
+#pragma unroll
+                    for (int k = j + 1; k < NB; k++) x[k] = fma(-lx, U[k][j], x[k]);
+#pragma unroll
+                    for (int r = j + 1; r < NB; r++) {
+                        const T l = U[r][j] * rd[j];
+#pragma unroll
+                        for (int k = j + 1; k <= r; k++) U[r][k] = fma(-l, U[k][j], U[r][k]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NB; k++)
+                    if (c0 + k <= i) as[i][c0 + k] = x[k];
+                if (i == c0) {
+#pragma unroll
+                    for (int j = 0; j < NB; j++) {
+                        rdv[c0 + j] = rd[j];
+                        dinv[c0 + j] = dev_sqrt<T>(rd[j]);  // 1 / L_jj = sqrt(1 / u_jj)
+                    }
+                    if (bad) *fail = 1;
+                }
+            }
+            __syncthreads();
+            // rank-8 update of everything right of the panel: u_ik -= sum_{j in panel} u_ij u_kj / u_jj
+            if (P + 1 < TILE / NB) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int k = tx + 16 * q;
+                    if (k >= c0 + NB) {
+                        T lk[NB];
+#pragma unroll
+                        for (int jj = 0; jj < NB; jj++) lk[jj] = as[k][c0 + jj] * rdv[c0 + jj];
+#pragma unroll
+                        for (int a = 0; a < 4; a++) {
+                            const int i = ty + 16 * a;
+                            if (i >= k) {
+                                T acc = T(0);
+#pragma unroll
+                                for (int jj = 0; jj < NB; jj++) acc = fma(as[i][c0 + jj], lk[jj], acc);
+                                as[i][k] -= acc;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        __syncthreads();
+        if (tid < TILE) {
+            T dj = as[tid][tid];
+            if (!(dj > T(0)) || !(dj <= T(1e300))) dj = T(1);
+            rdv[tid] = T(1) / dj;
+            dinv[tid] = T(1) / dev_sqrt<T>(dj);
+        }
+        __syncthreads();
+    }
+    // here: as (lower) = u, rdv = 1 / u_jj, dinv = 1 / L_jj, all visible (the loop ends on a barrier)
+    if (!(DBG & 2)) {
+        // ---- level 0: the eight 8x8 diagonal blocks, one column of the inverse per thread, in registers:
+        // x_i = (delta_ic - sum_{k < i} u_ik z_k) dinv_i with z_k = dinv_k x_k  (L_ik = u_ik dinv_k)
+        if (tid < TILE) {
+            const int c0 = tid & ~(NB - 1), c = tid & (NB - 1);
+            T z[NB];
+#pragma unroll
+            for (int i = 0; i < NB; i++) {
+                T s = (i == c) ? T(1) : T(0);
+#pragma unroll
+                for (int k = 0; k < i; k++) s = fma(-as[c0 + i][c0 + k], z[k], s);
+                const T di = dinv[c0 + i];
+                const T xi = s * di;
+                z[i] = xi * di;
+                if (i >= c) ws[c0 + i][c0 + c] = xi;
+            }
+        }
+        // ---- levels 1..3: half-width h = 8, 16, 32.  S = L21 W11 goes to the free upper-right block of `as`.
+#pragma unroll
+        for (int h = NB; h < TILE; h *= 2) {
+            const int cells = (TILE / (2 * h)) * h * h;  // 32 h: 256, 512, 1024
+            __syncthreads();
+            for (int e = tid; e < cells; e += 256) {
+                const int pr = e / (h * h), rc = e % (h * h), r = rc / h, c = rc % h, o = 2 * h * pr;
+                T acc = T(0);
+                for (int k = c; k < h; k++) acc = fma(as[o + h + r][o + k] * dinv[o + k], ws[o + k][o + c], acc);
+                as[o + r][o + h + c] = acc;
+            }
+            __syncthreads();
+            for (int e = tid; e < cells; e += 256) {
+                const int pr = e / (h * h), rc = e % (h * h), r = rc / h, c = rc % h, o = 2 * h * pr;
+                T acc = T(0);
+                for (int k = 0; k <= r; k++) acc = fma(ws[o + h + r][o + h + k], as[o + k][o + h + c], acc);
+                ws[o + h + r][o + c] = -acc;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // sum_i ln L_ii of a leaf (first warp), from dinv
 template <typename T>
 __device__ __forceinline__ void leaf_logdet(const T* dinv, int tid, T* out) {
@@ -329,7 +466,19 @@ __device__ __forceinline__ void leaf_logdet(const T* dinv, int tid, T* out) {
     }
 }
 
-template <typename T, int DBG = 0>  // DBG: probe-only switch (1: skip the Cholesky loops, 2: skip the inverse)
+// Leaf algorithm of k_leaf / k_node128: 0 = leaf_core, 1 = leaf_core_nb8 (register-resident 8-wide panels with FMA-pipe
+// updates: measured no faster than leaf_core in either precision, probes/leaf2_bench.cu — the gain needs the DMMA
+// products and the transposed layout of node_mma.cuh, which is what the f64 path runs)
+#ifndef HBEGP_LEAF_V
+#define HBEGP_LEAF_V 0
+#endif
+template <typename T, int DBG, int LV>
+__device__ __forceinline__ void leaf_core_sel(T (*as)[TILE + 1], T (*ws)[TILE + 1], T* rdv, T* dinv, int* fail, int tid) {
+    if constexpr (LV == 1) leaf_core_nb8<T, DBG>(as, ws, rdv, dinv, fail, tid);
+    else leaf_core<T, DBG>(as, ws, rdv, dinv, fail, tid);
+}
+
+template <typename T, int DBG = 0, int LV = HBEGP_LEAF_V>  // DBG: probe-only switch (1: skip the Cholesky loops, 2: skip the inverse)
 __global__ void __launch_bounds__(256) k_leaf(T* __restrict__ A, T* __restrict__ W, long mstride, int np, int r0,
                                               T* __restrict__ ldp, int ldp_stride, int* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char leaf_smem_raw[];
@@ -350,7 +499,7 @@ __global__ void __launch_bounds__(256) k_leaf(T* __restrict__ A, T* __restrict__
             const int i = ty + 16 * a, k = tx + 16 * q;
             as[i][k] = (k <= i) ? Ab[(long)i * np + k] : T(0);
         }
-    leaf_core<T, DBG>(as, ws, rdv, dinv, &fail, tid);
+    leaf_core_sel<T, DBG, LV>(as, ws, rdv, dinv, &fail, tid);
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -383,7 +532,7 @@ __device__ __forceinline__ void mm64(const T (*Am)[TILE + 1], const T (*Bm)[TILE
 // A whole 128-wide node of the recursion in one CTA (two leaves and the four 64^3 products between them), so that
 // the bottom level of the tree costs one launch instead of six dependent ones:
 //   W11 = leaf(A11); L21 = A21 W11^T; T = L21 W11; A22 -= L21 L21^T; W22 = leaf(A22); W21 = -W22 T.
-template <typename T>
+template <typename T, int LV = HBEGP_LEAF_V>
 __global__ void __launch_bounds__(256) k_node128(T* __restrict__ A, T* __restrict__ W, long mstride, int np, int r0,
                                                  T* __restrict__ ldp, int ldp_stride, int* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char leaf_smem_raw[];
@@ -409,7 +558,7 @@ __global__ void __launch_bounds__(256) k_node128(T* __restrict__ A, T* __restric
             as[i][k] = (k <= i) ? Ab[(long)i * np + k] : T(0);
             pm[i][k] = Ab[(long)(i + TILE) * np + k];  // A21
         }
-    leaf_core<T, 0>(as, w1, rdv, dinv, &fail, tid);
+    leaf_core_sel<T, 0, LV>(as, w1, rdv, dinv, &fail, tid);
     leaf_logdet<T>(dinv, tid, ld);
     T acc[4][4];
     // L21 = A21 W11^T
@@ -458,7 +607,7 @@ __global__ void __launch_bounds__(256) k_node128(T* __restrict__ A, T* __restric
 #pragma unroll
         for (int q = 0; q < 4; q++) pm[ty + 16 * a][tx + 16 * q] = acc[a][q];
     __syncthreads();
-    leaf_core<T, 0>(as, w2, rdv, dinv, &fail, tid);
+    leaf_core_sel<T, 0, LV>(as, w2, rdv, dinv, &fail, tid);
     leaf_logdet<T>(dinv, tid, ld + 1);
     // W21 = -W22 T
 #pragma unroll

@@ -23,6 +23,7 @@ if ROOT not in sys.path:
 
 N, D, RESTARTS = 1024, 8, 2
 FIXTURE = os.path.join(ROOT, "tests", "golden", "fit_spread_oracle.json")
+OTHER_OPTIMUM = 1e-2  # |d ln theta| beyond which two fits are different local optima, not the same one
 
 
 def problem(seed):
@@ -78,12 +79,20 @@ def run_gpu(out_path=None):
             table.append({"seed": seed, "lml_gpu": fk.lml, "lml_oracle": ref["lml"],
                           "d_lml_rel": abs(fk.lml - ref["lml"]) / abs(ref["lml"]),
                           "d_lml_same_theta_rel": abs(float(lml_at_ref[0]) - ref["lml"]) / abs(ref["lml"]),
-                          "max_d_ln_theta": float(np.abs(theta - tref).max()),
+                          "max_d_ln_theta": float(np.abs(theta - tref).max()), "theta_gpu": [float(v) for v in theta],
                           "evals_gpu": int(fk.n_evals), "evals_oracle": ref["n_evals"]})
             fk.model.close()
-    worst = {k: max(r[k] for r in table) for k in ("d_lml_rel", "d_lml_same_theta_rel", "max_d_ln_theta")}
+    # A fit whose theta is far from the oracle's ended in a DIFFERENT local optimum: one of its L-BFGS runs branched into
+    # another basin.  That is a property of the optimiser on this objective, not of the evaluation (the same seed flips
+    # when the rounding of the factorisation changes in the 13th digit); such seeds are listed
+    # apart and the caller checks them against the oracle at the GPU's own theta.
+    same = [r for r in table if r["max_d_ln_theta"] <= OTHER_OPTIMUM]
+    other = [r for r in table if r["max_d_ln_theta"] > OTHER_OPTIMUM]
+    worst = {k: max(r[k] for r in same) for k in ("d_lml_rel", "max_d_ln_theta")}
+    worst["d_lml_same_theta_rel"] = max(r["d_lml_same_theta_rel"] for r in table)
     med = {k: float(np.median([r[k] for r in table])) for k in ("d_lml_rel", "d_lml_same_theta_rel", "max_d_ln_theta")}
-    out = {"n": N, "d": D, "restarts": RESTARTS, "seeds": len(table), "worst": worst, "median": med, "rows": table}
+    out = {"n": N, "d": D, "restarts": RESTARTS, "seeds": len(table), "same_optimum": len(same), "worst": worst, "median": med,
+           "other_optimum": other, "rows": table}
     if out_path:
         json.dump(out, open(out_path, "w"), indent=1)
     return out
@@ -94,4 +103,4 @@ if __name__ == "__main__":
         run_oracle(int(sys.argv[2]) if len(sys.argv) > 2 else 0, int(sys.argv[3]) if len(sys.argv) > 3 else 20)
     else:
         res = run_gpu(os.path.join(ROOT, "gpurun_out", "r02_fit_spread.json"))
-        print(json.dumps({k: res[k] for k in ("seeds", "worst", "median")}))
+        print(json.dumps({k: res[k] for k in ("seeds", "same_optimum", "worst", "median", "other_optimum")}))
