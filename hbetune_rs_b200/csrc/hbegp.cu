@@ -148,7 +148,7 @@ struct EngineBase {
     bool use_side = true;
     int side_max_cnt = 4;  // also use the side stream at n > 2048 for groups of at most this many matrices
     bool use_node128 = true;
-    int node_v = 2;  // f64 bottom node: 2 = k_node128_v2 (register-resident panels + DMMA products), 1 = k_node128
+    int node_v = 2;  // bottom node: 2 = k_node128_v2 (register-resident panels + DMMA products, FP64 inside), 1 = k_node128
     cudaEvent_t fork_ev = nullptr;
     long n = 0;
     int d = 0, np = 0;
@@ -459,13 +459,11 @@ struct Engine : EngineBase {
             return HBEGP_OK;
         }
         if (s == 2 * TILE && use_node128) {  // the bottom node of the tree in one launch
-            if constexpr (std::is_same<T, double>::value) {
-                if (node_v == 2) {
-                    CUDA_TRY(launch_prio(k_node128_v2<false>, dim3(1, 1, cnt), dim3(256), node128_v2_smem_bytes(), st, Ab, Wb, mstride(), np, r0,
-                                         (T*)ldp.p + (size_t)s0 * (np / TILE), np / TILE, (int*)d_status.p + s0, (long long*)nullptr));
-                    launches++;
-                    return HBEGP_OK;
-                }
+            if (node_v == 2) {  // FP64 arithmetic inside for both precisions (node_mma.cuh)
+                CUDA_TRY(launch_prio(k_node128_v2<false, T>, dim3(1, 1, cnt), dim3(256), node128_v2_smem_bytes(), st, Ab, Wb, mstride(), np, r0,
+                                     (T*)ldp.p + (size_t)s0 * (np / TILE), np / TILE, (int*)d_status.p + s0, (long long*)nullptr));
+                launches++;
+                return HBEGP_OK;
             }
             CUDA_TRY(launch_prio(k_node128<T>, dim3(1, 1, cnt), dim3(256), node128_smem_bytes<T>(), st, Ab, Wb, mstride(), np, r0,
                                  (T*)ldp.p + (size_t)s0 * (np / TILE), np / TILE, (int*)d_status.p + s0));
@@ -1464,8 +1462,7 @@ static int configure_gemms() {
     const int big = (int)kMaxFeatureSmem;
     CUDA_TRY(cudaFuncSetAttribute(k_leaf<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem_bytes<T>()));
     CUDA_TRY(cudaFuncSetAttribute(k_node128<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)node128_smem_bytes<T>()));
-    if constexpr (std::is_same<T, double>::value)
-        CUDA_TRY(cudaFuncSetAttribute(k_node128_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)node128_v2_smem_bytes()));
+    CUDA_TRY(cudaFuncSetAttribute(k_node128_v2<false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)node128_v2_smem_bytes()));
     CUDA_TRY(cudaFuncSetAttribute(k_assemble<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(k_assemble<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(k_assemble<T, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));

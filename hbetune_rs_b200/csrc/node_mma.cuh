@@ -302,9 +302,13 @@ __device__ __forceinline__ void prod_w_b(const RowT* Wl, const RowT* Bm, double 
 }
 
 //   W11 = leaf(A11); L21 = A21 W11^T; A22 -= L21 L21^T; T = L21 W11; W22 = leaf(A22); W21 = -W22 T.
-template <bool PROF = false>
-__global__ void __launch_bounds__(256) k_node128_v2(double* __restrict__ A, double* __restrict__ W, long mstride, int np, int r0g,
-                                                    double* __restrict__ ldp, int ldp_stride, int* __restrict__ status,
+// TIO is the type of the matrices in global memory.  The arithmetic inside the node is FP64 in both cases: for --use-32
+// (TIO = float) the block is widened on load and rounded once on store — the node is latency bound, not FP64-rate bound,
+// so this costs nothing (35 us against 52 us for the FP32 k_node128) and the bottom of the recursion adds no FP32
+// rounding of its own.
+template <bool PROF = false, typename TIO = double>
+__global__ void __launch_bounds__(256) k_node128_v2(TIO* __restrict__ A, TIO* __restrict__ W, long mstride, int np, int r0g,
+                                                    TIO* __restrict__ ldp, int ldp_stride, int* __restrict__ status,
                                                     long long* __restrict__ prof = nullptr) {
     extern __shared__ __align__(16) unsigned char leaf_smem_raw[];
     RowT* at = reinterpret_cast<RowT*>(leaf_smem_raw);                              // the block being factored, transposed
@@ -317,9 +321,9 @@ __global__ void __launch_bounds__(256) k_node128_v2(double* __restrict__ A, doub
     __shared__ int fail;
     const int b = blockIdx.z, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
-    double* Ab = A + (long)b * mstride + (long)r0g * np + r0g;
-    double* Wb = W + (long)b * mstride + (long)r0g * np + r0g;
-    double* ld = ldp + (long)b * ldp_stride + r0g / TILE;
+    TIO* Ab = A + (long)b * mstride + (long)r0g * np + r0g;
+    TIO* Wb = W + (long)b * mstride + (long)r0g * np + r0g;
+    TIO* ld = ldp + (long)b * ldp_stride + r0g / TILE;
     if (tid == 0) fail = 0;
     long long* tp = PROF ? prof + (long)b * 64 : nullptr;
     HBEGP_STAMP();
@@ -329,10 +333,10 @@ __global__ void __launch_bounds__(256) k_node128_v2(double* __restrict__ A, doub
         for (int q = 0; q < 4; q++) {
             const int i = ty + 16 * a, k = tx + 16 * q;
             if (k <= i) {
-                at[k][i] = Ab[(long)i * np + k];
-                w2[k][i] = Ab[(long)(i + TILE) * np + TILE + k];  // A22, transposed as well
+                at[k][i] = (double)Ab[(long)i * np + k];
+                w2[k][i] = (double)Ab[(long)(i + TILE) * np + TILE + k];  // A22, transposed as well
             }
-            pm[i][k] = Ab[(long)(i + TILE) * np + k];  // A21
+            pm[i][k] = (double)Ab[(long)(i + TILE) * np + k];  // A21
         }
     HBEGP_STAMP();
     double rdprod1, rdprod2;
@@ -379,17 +383,20 @@ __global__ void __launch_bounds__(256) k_node128_v2(double* __restrict__ A, doub
     // W21 = -W22 T, straight to global memory
     prod_w_b(w2, pm, acc, warp, lr, lc);
 #pragma unroll
-    for (int i = 0; i < 8; i++)
-        *reinterpret_cast<double2*>(&Wb[(long)(8 * i + lr + TILE) * np + 8 * warp + 2 * lc]) = make_double2(-acc[i][0], -acc[i][1]);
+    for (int i = 0; i < 8; i++) {
+        TIO* dst = &Wb[(long)(8 * i + lr + TILE) * np + 8 * warp + 2 * lc];
+        if constexpr (sizeof(TIO) == 8) *reinterpret_cast<double2*>(dst) = make_double2(-acc[i][0], -acc[i][1]);
+        else *reinterpret_cast<float2*>(dst) = make_float2((float)-acc[i][0], (float)-acc[i][1]);
+    }
     HBEGP_STAMP();
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int i = ty + 16 * a, k = tx + 16 * q;
-            Wb[(long)i * np + k] = w1[i][k];                 // zeros above the diagonal
-            Wb[(long)i * np + TILE + k] = 0.0;               // (0,1) block: read by the 128-wide GEMM tiles' triangular k ranges
-            Wb[(long)(i + TILE) * np + TILE + k] = w2[i][k];
+            Wb[(long)i * np + k] = (TIO)w1[i][k];            // zeros above the diagonal
+            Wb[(long)i * np + TILE + k] = TIO(0);            // (0,1) block: read by the 128-wide GEMM tiles' triangular k ranges
+            Wb[(long)(i + TILE) * np + TILE + k] = (TIO)w2[i][k];
         }
     // sum ln L_kk = -1/2 ln prod 1 / u_kk: the eight partial products per half sit in threads 64 + 24 j
     {
@@ -403,7 +410,7 @@ __global__ void __launch_bounds__(256) k_node128_v2(double* __restrict__ A, doub
             double s = 0.0;
 #pragma unroll
             for (int j = 0; j < 8; j++) s += rdv[8 * tid + j];
-            ld[tid] = s;
+            ld[tid] = (TIO)s;
         }
     }
     if (tid == 0 && fail) status[b] = 1;

@@ -38,12 +38,12 @@ float run(int B, const T* A0, T* A, T* W, int np, T* ldp, int* st, int reps) {
 float run_v2(int B, const double* A0, double* A, double* W, int np, double* ldp, int* st, int reps) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     size_t bytes = (size_t)B * np * np * sizeof(double), smem = node128_v2_smem_bytes();
-    CK(cudaFuncSetAttribute(k_node128_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k_node128_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_node128_v2<false, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_node128_v2<true, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         long long* prof; CK(cudaMalloc(&prof, B * 64 * 8)); CK(cudaMemset(prof, 0, B * 64 * 8));
         CK(cudaMemcpy(A, A0, bytes, cudaMemcpyDeviceToDevice));
-        k_node128_v2<true><<<dim3(1, 1, B), 256, smem>>>(A, W, (long)np * np, np, 0, ldp, np / 64, st, prof);
+        k_node128_v2<true, double><<<dim3(1, 1, B), 256, smem>>>(A, W, (long)np * np, np, 0, ldp, np / 64, st, prof);
         CK(cudaDeviceSynchronize());
         long long h[64]; CK(cudaMemcpy(h, prof, 64 * 8, cudaMemcpyDeviceToHost));
         const char* names[] = {"load", "chol1", "lvl0_1", "lvls1", "L21", "syrk+T", "chol2", "lvl0_2", "lvls2", "W21", "store+logdet"};
@@ -65,7 +65,7 @@ float run_v2(int B, const double* A0, double* A, double* W, int np, double* ldp,
         CK(cudaMemset(st, 0, B * sizeof(int)));
         CK(cudaDeviceSynchronize());
         cudaEventRecord(e0);
-        k_node128_v2<false><<<dim3(1, 1, B), 256, smem>>>(A, W, (long)np * np, np, 0, ldp, np / 64, st, nullptr);
+        k_node128_v2<false, double><<<dim3(1, 1, B), 256, smem>>>(A, W, (long)np * np, np, 0, ldp, np / 64, st, nullptr);
         cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
         CK(cudaGetLastError());
         float ms; cudaEventElapsedTime(&ms, e0, e1);
