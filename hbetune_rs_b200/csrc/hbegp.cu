@@ -148,6 +148,7 @@ struct EngineBase {
     bool use_side = true;
     int side_max_cnt = 4;  // also use the side stream at n > 2048 for groups of at most this many matrices
     bool use_node128 = true;
+    int group_min = 4;  // n <= 2048: fewest matrices per stream group (HBEGP_GROUP_MIN)
     int node_v = 2;  // bottom node: 2 = k_node128_v2 (register-resident panels + DMMA products, FP64 inside), 1 = k_node128
     cudaEvent_t fork_ev = nullptr;
     long n = 0;
@@ -600,7 +601,7 @@ struct Engine : EngineBase {
             // 1 / 2 / 4 / 8 groups): n = 512: 0.669 / 0.639 / 0.640 / 0.631; n = 1024: 2.47 / 2.32 / 2.26 / 2.20;
             // n = 2048: 12.59 / 12.23 / 12.07 / 11.89 -- the latency-bound bottom nodes of one group (a few dozen CTAs on
             // 148 SMs) overlap another group's GEMMs.  A group of fewer than 4 small matrices is all launch overhead.
-            if (np <= 2048) g = std::min(g, std::max(1, cnt / 4));
+            if (np <= 2048) g = std::min(g, std::max(1, cnt / group_min));
             else g = std::min(g, 4);
         }
         return std::max(1, std::min(g, cnt));
@@ -1763,7 +1764,8 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
         int rc = (dtype == HBEGP_F64) ? configure_gemms<double>() : configure_gemms<float>();
         if (rc) { delete e; return rc; }
     }
-    int nsub = 8;
+    int nsub = 16;
+    if (const char* s = getenv("HBEGP_NSUB")) nsub = std::max(1, std::min(16, atoi(s)));
     bool forced = false;
     if (const char* s = getenv("HBEGP_STREAMS")) { nsub = std::max(1, std::min(16, atoi(s))); forced = true; }
     {
@@ -1820,6 +1822,7 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
     if (const char* s = getenv("HBEGP_SIDE")) e->use_side = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_NODE128")) e->use_node128 = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_NODE_V")) e->node_v = atoi(s);
+    if (const char* s = getenv("HBEGP_GROUP_MIN")) e->group_min = std::max(1, atoi(s));
     if (const char* s = getenv("HBEGP_SIDE_CNT")) e->side_max_cnt = atoi(s);
     if (const char* s = getenv("HBEGP_PAD")) {
         const bool pad = atoi(s) != 0;

@@ -6,7 +6,7 @@ import os, sys, json, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 SHAPES = [(1024, 8, 32, "f64"), (1024, 8, 32, "f32"), (512, 8, 32, "f64"), (2048, 16, 32, "f64"), (4096, 16, 8, "f64"),
-          (4096, 16, 64, "f64"), (4096, 16, 64, "f32"), (4096, 16, 8, "f32")]
+          (4096, 16, 64, "f64"), (4096, 16, 64, "f32"), (4096, 16, 8, "f32"), (1024, 8, 8, "f64"), (500, 8, 2, "f64"), (2048, 16, 8, "f64")]
 
 def child():
     import argparse, bench
