@@ -148,7 +148,7 @@ struct EngineBase {
     bool use_side = true;
     int side_max_cnt = 4;  // also use the side stream at n > 2048 for groups of at most this many matrices
     bool use_node128 = true;
-    int group_min = 4;  // n <= 2048: fewest matrices per stream group (HBEGP_GROUP_MIN)
+    int group_min = 0;  // n <= 2048: fewest matrices per stream group (HBEGP_GROUP_MIN; 0 = by size)
     int node_v = 2;  // bottom node: 2 = k_node128_v2 (register-resident panels + DMMA products, FP64 inside), 1 = k_node128
     cudaEvent_t fork_ev = nullptr;
     long n = 0;
@@ -600,8 +600,11 @@ struct Engine : EngineBase {
             // Re-measured in round 2 (profiles/r02_c3_streams.log, r02_streams_sweep.log; B = 33, ms per step with
             // 1 / 2 / 4 / 8 groups): n = 512: 0.669 / 0.639 / 0.640 / 0.631; n = 1024: 2.47 / 2.32 / 2.26 / 2.20;
             // n = 2048: 12.59 / 12.23 / 12.07 / 11.89 -- the latency-bound bottom nodes of one group (a few dozen CTAs on
-            // 148 SMs) overlap another group's GEMMs.  A group of fewer than 4 small matrices is all launch overhead.
-            if (np <= 2048) g = std::min(g, std::max(1, cnt / group_min));
+            // 148 SMs) overlap another group's GEMMs.  With the faster bottom node (node_mma.cuh) up to 16 groups of as few
+            // as 2 matrices (1 from n = 1024 up) pay off (profiles/r02_group_min.log: n = 1024 B = 33 1.786 -> 1.750 ms,
+            // n = 2048 B = 9 3.70 -> 3.39, n = 500 B = 3 unchanged).
+            const int gm = group_min > 0 ? group_min : (np >= 1024 ? 1 : 2);
+            if (np <= 2048) g = std::min(g, std::max(1, cnt / gm));
             else g = std::min(g, 4);
         }
         return std::max(1, std::min(g, cnt));
@@ -1822,7 +1825,7 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
     if (const char* s = getenv("HBEGP_SIDE")) e->use_side = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_NODE128")) e->use_node128 = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_NODE_V")) e->node_v = atoi(s);
-    if (const char* s = getenv("HBEGP_GROUP_MIN")) e->group_min = std::max(1, atoi(s));
+    if (const char* s = getenv("HBEGP_GROUP_MIN")) e->group_min = std::max(0, atoi(s));
     if (const char* s = getenv("HBEGP_SIDE_CNT")) e->side_max_cnt = atoi(s);
     if (const char* s = getenv("HBEGP_PAD")) {
         const bool pad = atoi(s) != 0;
