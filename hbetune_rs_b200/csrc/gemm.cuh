@@ -51,6 +51,9 @@ struct GemmArgs {
     // K_LE_N only: rasterise in groups of `raster_group` row tiles (all column tiles of a group before the
     // next group) so that the group's A rows stay in L2 while B streams; 0 = plain column-major order.
     int raster_group;
+    // Host-side hint (unused by the kernel): run on 32x32 tiles when the 64x64 grid would have at most this many CTAs
+    // (see launch_gemm); 0 = never.
+    long small_ctas;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -424,9 +427,24 @@ inline int pick_gemm_tile(int M, int N) {
 template <typename T>
 constexpr int wm128() { return 64; }
 
+// Latency-bound products (the bottom levels of the recursion at small n, small batches): a 64x64 tile puts its whole k
+// loop on ONE SM's FP64 pipe (0.52 us per 16-k step) while most of the 148 SMs idle.  When the caller allows it
+// (GemmArgs::small_ctas) and the 64x64 grid would have at most that many CTAs, the product runs on 32x32 tiles instead
+// (4 warps of 16x16; four times the CTAs, a quarter of the k-loop time each).  Same bits: every output element sees
+// the same sequence of k4 steps, the tiles only differ in how many structural zeros they multiply.  FP64 only (the FFMA
+// micro-kernel needs 32-wide warp tiles).  Measured (profiles/r02_small_tile.log, ms per batched evaluation, off -> 296):
+// n = 500 B = 3 0.300 -> 0.257, n = 512 B = 33 0.474 -> 0.427, n = 1024 B = 9 0.875 -> 0.786, n = 1024 B = 33 1.751 ->
+// 1.722; at n >= 2048 the GPU is busy with other groups' large products and the less efficient tile costs 1-1.5 %,
+// so the engine only allows it up to n = 1024.
 template <typename T, bool AK, bool BK_>
 inline cudaError_t launch_gemm(const GemmArgs<T>& a, int batch, cudaStream_t stream) {
     if (pick_gemm_tile<T>(a.M, a.N) == 128) return launch_gemm_cfg<T, 128, 128, wm128<T>(), 32, AK, BK_>(a, batch, stream);
+    if constexpr (std::is_same<T, double>::value) {
+        const long tm = a.M / 64, tn = a.N / 64;
+        const long tiles = a.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+        if (a.rowsumsq == nullptr && a.raster_group == 0 && tiles * batch <= a.small_ctas)
+            return launch_gemm_cfg<T, 32, 32, 16, 16, AK, BK_>(a, batch, stream);
+    }
     return launch_gemm_cfg<T, 64, 64, 32, 32, AK, BK_>(a, batch, stream);
 }
 

@@ -148,6 +148,8 @@ struct EngineBase {
     bool use_side = true;
     int side_max_cnt = 4;  // also use the side stream at n > 2048 for groups of at most this many matrices
     bool use_node128 = true;
+    long small_tile_ctas = 296;  // 32x32 GEMM tiles for grids of at most this many 64x64 CTAs ...
+    int small_tile_np = 1024;    // ... at n up to this (HBEGP_SMALL_TILE_CTAS, HBEGP_SMALL_TILE_NP; gemm.cuh launch_gemm)
     int group_min = 0;  // n <= 2048: fewest matrices per stream group (HBEGP_GROUP_MIN; 0 = by size)
     int node_v = 2;  // bottom node: 2 = k_node128_v2 (register-resident panels + DMMA products, FP64 inside), 1 = k_node128
     cudaEvent_t fork_ev = nullptr;
@@ -495,6 +497,7 @@ struct Engine : EngineBase {
         g.lda = g.ldb = g.ldc = np;
         g.sA = g.sB = g.sC = mstride();
         g.rowsumsq = nullptr;
+        g.small_ctas = np <= small_tile_np ? small_tile_ctas : 0;
         // 1. panel solve as a product with the inverse: L21 = A21 W11^T  -> W(2,1)
         g.A = A21; g.B = W11; g.C = W21; g.M = s2; g.N = s1; g.K = s1; g.kmode = K_LE_N; g.lower_only = 0;
         g.alpha = T(1); g.beta = T(0);
@@ -532,6 +535,7 @@ struct Engine : EngineBase {
         g.A = Wb; g.B = Wb; g.C = Ab; g.M = np; g.N = np; g.K = np; g.kmode = K_GE_M; g.lower_only = 1;
         g.alpha = T(1); g.beta = T(0);
         g.rowsumsq = nullptr;
+        g.small_ctas = np <= small_tile_np ? small_tile_ctas : 0;
         CUDA_TRY((launch_gemm_auto<T, false, false>(g, cnt, st, aligned128(), 4))); launches++;
         return HBEGP_OK;
     }
@@ -1456,6 +1460,11 @@ static int configure_gemms() {
     HBEGP_CFG(64, 64, 32, 32, true, true);
     HBEGP_CFG(64, 64, 32, 32, true, false);
     HBEGP_CFG(64, 64, 32, 32, false, false);
+    if constexpr (std::is_same<T, double>::value) {
+        HBEGP_CFG(32, 32, 16, 16, true, true);
+        HBEGP_CFG(32, 32, 16, 16, true, false);
+        HBEGP_CFG(32, 32, 16, 16, false, false);
+    }
 #undef HBEGP_CFG
     if (std::is_same<T, float>::value) {
         CUDA_TRY((tf32::configure<true, true>()));
@@ -1825,6 +1834,8 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
     if (const char* s = getenv("HBEGP_SIDE")) e->use_side = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_NODE128")) e->use_node128 = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_NODE_V")) e->node_v = atoi(s);
+    if (const char* s = getenv("HBEGP_SMALL_TILE_CTAS")) e->small_tile_ctas = atol(s);
+    if (const char* s = getenv("HBEGP_SMALL_TILE_NP")) e->small_tile_np = atoi(s);
     if (const char* s = getenv("HBEGP_GROUP_MIN")) e->group_min = std::max(0, atoi(s));
     if (const char* s = getenv("HBEGP_SIDE_CNT")) e->side_max_cnt = atoi(s);
     if (const char* s = getenv("HBEGP_PAD")) {

@@ -69,10 +69,23 @@ __device__ __forceinline__ void leaf_mma(RowT* at, RowT* ws, double* rdv, double
     for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int q = 0; q < 4; q++) ws[ty + 16 * a][tx + 16 * q] = 0.0;
-    // this warp's tiles of the trailing updates: tile t = warp + 8 s of the lower triangle, the same for every panel
+    // Tiles of the rank-8 trailing update after panel P, relative to its first tile (c0 + 8, c0 + 8):
+    //  * column 0 — the rows the NEXT panel reads — belongs to the two panel warps (tile rows w, w + 2, ..), which update
+    //    it and go straight on to the next panel's pivot chain (look-ahead);
+    //  * the rest (tile rows/columns >= 1, a lower triangle again) is dealt to warps 2..7 (tile t = (warp - 2) + 6 s) and
+    //    runs underneath that chain, together with the scaling of the panel before.
     int ttr[4], ttc[4];
 #pragma unroll
-    for (int s = 0; s < 4; s++) lower_tile_of(warp + 8 * s, ttr[s], ttc[s]);
+    for (int s = 0; s < 4; s++) {
+        if (warp < 2) {
+            ttr[s] = warp + 2 * s;
+            ttc[s] = 0;
+        } else {
+            lower_tile_of(warp - 2 + 6 * s, ttr[s], ttc[s]);
+            ttr[s] += 1;
+            ttc[s] += 1;
+        }
+    }
     rdprod = 1.0;
     // finishes panel P (rows c0 .. c0 + 7 of `at`): true factor L_ik = u_ik / L_kk, 1 / L_kk = sqrt(1 / u_kk)
     auto finish_panel = [&](int c0, int idx) {  // idx = 0 .. 191
@@ -84,88 +97,108 @@ __device__ __forceinline__ void leaf_mma(RowT* at, RowT* ws, double* rdv, double
         }
         for (int i = k + 1 + l24; i < TILE; i += 24) at[k][i] *= dk;
     };
-    // ---- Cholesky on unscaled columns u_ij = L_ij L_jj:  u_ik -= u_ij u_kj / u_jj
-    for (int P = 0; P < NP; P++) {
-        const int c0 = NB * P;
-        __syncthreads();
-        if (PROF && tid == 0) pp[2 * P] = clock64();
-        if (tid < TILE) {  // warps 0 and 1: one row of the panel per thread
-            const int i = tid;
-            double U[NB][NB], x[NB], rd[NB];
+    // one panel: rows c0 .. c0 + 7 of `at`, one row of the (untransposed) panel per thread of warps 0 and 1
+    auto eliminate_panel = [&](int c0) {
+        const int i = tid;
+        double U[NB][NB], x[NB], rd[NB];
 #pragma unroll
-            for (int r = 0; r < NB; r++)
+        for (int r = 0; r < NB; r++)
 #pragma unroll
-                for (int k = 0; k <= r; k++) U[r][k] = at[c0 + k][c0 + r];
+            for (int k = 0; k <= r; k++) U[r][k] = at[c0 + k][c0 + r];
 #pragma unroll
-            for (int k = 0; k < NB; k++) x[k] = at[c0 + k][i];
-            // the diagonal rows are overwritten below by their owners: every row thread must hold its copy first
-            asm volatile("bar.sync 1, 64;" ::: "memory");
-            if (i >= c0) {
-                bool bad = false;
+        for (int k = 0; k < NB; k++) x[k] = at[c0 + k][i];
+        // the diagonal rows are overwritten below by their owners: every row thread must hold its copy first
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        if (i >= c0) {
+            bool bad = false;
 #pragma unroll
-                for (int j = 0; j < NB; j++) {
-                    // A non-positive (or non-finite) pivot is recorded, not repaired: the test stays off the dependent
-                    // chain and whatever follows in this matrix is discarded with status = 1 (lml.rs:47-50).
-                    const double dj = U[j][j];
-                    bad |= !(dj > 0.0) || !(dj <= 1e300);
-                    const double r_ = pivot_rcp3(dj);
-                    rd[j] = r_;
+            for (int j = 0; j < NB; j++) {
+                // A non-positive (or non-finite) pivot is recorded, not repaired: the test stays off the dependent
+                // chain and whatever follows in this matrix is discarded with status = 1 (lml.rs:47-50).
+                const double dj = U[j][j];
+                bad |= !(dj > 0.0) || !(dj <= 1e300);
+                const double r_ = pivot_rcp3(dj);
+                rd[j] = r_;
 #pragma unroll
-                    for (int r = j + 1; r < NB; r++) {
-                        const double l = U[r][j] * r_;
+                for (int r = j + 1; r < NB; r++) {
+                    const double l = U[r][j] * r_;
 #pragma unroll
-                        for (int k = j + 1; k <= r; k++) U[r][k] = fma(-l, U[k][j], U[r][k]);
-                    }
-                    const double lx = x[j] * r_;
-#pragma unroll
-                    for (int k = j + 1; k < NB; k++) x[k] = fma(-lx, U[k][j], x[k]);
+                    for (int k = j + 1; k <= r; k++) U[r][k] = fma(-l, U[k][j], U[r][k]);
                 }
+                const double lx = x[j] * r_;
 #pragma unroll
-                for (int k = 0; k < NB; k++)
-                    if (c0 + k <= i) at[c0 + k][i] = x[k];
-                if (i == c0) {
-#pragma unroll
-                    for (int j = 0; j < NB; j++) rdv[c0 + j] = rd[j];
-                    if (bad) *fail = 1;
-                }
+                for (int k = j + 1; k < NB; k++) x[k] = fma(-lx, U[k][j], x[k]);
             }
-        } else if (P > 0) {
-            finish_panel(c0 - NB, tid - TILE);  // warps 2..7, idle otherwise: the previous panel is final
-        } else if (pending_log != nullptr && (tid - TILE) % 24 == 0) {
-            *pending_log = -0.5 * log(*pending_log);  // the previous leaf's log-determinant part, off the critical path
+#pragma unroll
+            for (int k = 0; k < NB; k++)
+                if (c0 + k <= i) at[c0 + k][i] = x[k];
+            if (i == c0) {
+#pragma unroll
+                for (int j = 0; j < NB; j++) rdv[c0 + j] = rd[j];
+                if (bad) *fail = 1;
+            }
         }
-        __syncthreads();
-        if (PROF && tid == 0) pp[2 * P + 1] = clock64();
-        // rank-8 update of the tiles right of the panel on the DMMA pipe: C'[k'][i] -= sum_j (u_k'j / u_jj) u_ij
-        const int nt = NP - 1 - P, ntiles = nt * (nt + 1) / 2;
-        {
-            double2 c[4];
-            double2* cp[4];
-            double a[4][2], bq[4][2];
-            const double r0 = rdv[c0 + lc], r1 = rdv[c0 + 4 + lc];
+    };
+    // this warp's share of the rank-8 update after panel c0 on the DMMA pipe: C'[k'][i] -= sum_j (u_k'j / u_jj) u_ij.
+    // All operand loads are unconditional (clamped tiles) so that they issue back to back; only the DMMAs and the
+    // stores of tiles outside the remaining triangle are predicated off.
+    auto trailing = [&](int c0, int nt) {
+        double2 c[4];
+        double2* cp[4];
+        double a[4][2], bq[4][2];
+        bool on[4];
+        const double r0 = rdv[c0 + lc], r1 = rdv[c0 + 4 + lc];
 #pragma unroll
-            for (int s = 0; s < 4; s++) {
-                if (warp + 8 * s < ntiles) {
-                    const int row0 = c0 + NB + 8 * ttr[s], col0 = c0 + NB + 8 * ttc[s];
-                    cp[s] = reinterpret_cast<double2*>(&at[col0 + lr][row0 + 2 * lc]);
-                    c[s] = *cp[s];
-                    a[s][0] = -(at[c0 + lc][col0 + lr] * r0);
-                    a[s][1] = -(at[c0 + 4 + lc][col0 + lr] * r1);
-                    bq[s][0] = at[c0 + lc][row0 + lr];
-                    bq[s][1] = at[c0 + 4 + lc][row0 + lr];
-                }
-            }
+        for (int s = 0; s < 4; s++) {
+            on[s] = ttr[s] < nt;
+            const int row0 = c0 + NB + 8 * (on[s] ? ttr[s] : 0), col0 = c0 + NB + 8 * (on[s] ? ttc[s] : 0);
+            cp[s] = reinterpret_cast<double2*>(&at[col0 + lr][row0 + 2 * lc]);
+            c[s] = *cp[s];
+            a[s][0] = at[c0 + lc][col0 + lr];
+            a[s][1] = at[c0 + 4 + lc][col0 + lr];
+            bq[s][0] = at[c0 + lc][row0 + lr];
+            bq[s][1] = at[c0 + 4 + lc][row0 + lr];
+        }
 #pragma unroll
-            for (int h = 0; h < 2; h++)
+        for (int s = 0; s < 4; s++) {
+            a[s][0] = -(a[s][0] * r0);
+            a[s][1] = -(a[s][1] * r1);
+        }
 #pragma unroll
-                for (int s = 0; s < 4; s++)
-                    if (warp + 8 * s < ntiles) dmma_acc(c[s].x, c[s].y, a[s][h], bq[s][h]);
+        for (int h = 0; h < 2; h++)
 #pragma unroll
             for (int s = 0; s < 4; s++)
-                if (warp + 8 * s < ntiles) *cp[s] = c[s];
+                if (on[s]) dmma_acc(c[s].x, c[s].y, a[s][h], bq[s][h]);
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+            if (on[s]) *cp[s] = c[s];
+    };
+    // ---- Cholesky on unscaled columns u_ij = L_ij L_jj:  u_ik -= u_ij u_kj / u_jj
+    // Iteration P: [warps 0, 1] column 0 of the update after panel P, then panel P + 1;  [warps 2..7] the rest of that
+    // update and the scaling of panel P - 1.  P = -1 is the prologue (panel 0 only; one copy of the code for both).
+    for (int P = -1; P + 1 < NP; P++) {
+        const int c0 = NB * P, nt = NP - 1 - P;
+        __syncthreads();  // panel P is in place; the update after panel P - 1 is complete
+        if (PROF && tid == 0) pp[P + 1] = clock64();
+        if (tid < TILE) {
+            if (P >= 0) {
+                trailing(c0, nt);  // tile column 0: the next panel's rows
+                asm volatile("bar.sync 1, 64;" ::: "memory");
+            }
+            eliminate_panel(c0 + NB);
+        } else {
+            if (P >= 0) trailing(c0, nt);                        // the rest, underneath the next panel's chain
+            if (P > 0) finish_panel(c0 - NB, tid - TILE);        // panel P - 1 is not read any more
+            if (P < 0 && pending_log != nullptr && (tid - TILE) % 24 == 0)
+                *pending_log = -0.5 * log(*pending_log);  // the previous leaf's log-determinant part, off the critical path
         }
     }
-    if (tid >= TILE) finish_panel(TILE - NB, tid - TILE);  // the last panel (rdv is visible: the loop ends on a barrier)
+    __syncthreads();
+    if (PROF && tid == 0) pp[NP] = clock64();
+    if (tid >= TILE) {
+        finish_panel(TILE - 2 * NB, tid - TILE);
+        finish_panel(TILE - NB, tid - TILE);
+    }
     __syncthreads();
     HBEGP_STAMP();
     // ---- inverse, level 0: the eight 8x8 diagonal blocks, one column per thread, in registers

@@ -52,8 +52,8 @@ float run_v2(int B, const double* A0, double* A, double* W, int np, double* ldp,
         printf(" | total %lld\n", h[11] - h[0]);
         for (int leaf = 0; leaf < 2; leaf++) {
             const long long* q = h + (leaf ? 40 : 16);
-            printf("   leaf %d panels (step/trailing cycles):", leaf + 1);
-            for (int P = 0; P < 8; P++) printf(" %lld/%lld", q[2 * P + 1] - q[2 * P], P < 7 ? q[2 * P + 2] - q[2 * P + 1] : 0LL);
+            printf("   leaf %d panel iterations (cycles):", leaf + 1);
+            for (int P = 0; P < 8; P++) printf(" %lld", q[P + 1] - q[P]);  // prologue (panel 0), then iterations 0..6
             printf("\n");
         }
         cudaFree(prof);
