@@ -150,6 +150,7 @@ struct EngineBase {
     bool use_node128 = true;
     long small_tile_ctas = 296;  // 32x32 GEMM tiles for grids of at most this many 64x64 CTAs ...
     int small_tile_np = 1024;    // ... at n up to this (HBEGP_SMALL_TILE_CTAS, HBEGP_SMALL_TILE_NP; gemm.cuh launch_gemm)
+    bool small_tile_kinv = true;  // also for K^-1 = W^T W (HBEGP_SMALL_TILE_KINV)
     int group_min = 0;  // n <= 2048: fewest matrices per stream group (HBEGP_GROUP_MIN; 0 = by size)
     int node_v = 2;  // bottom node: 2 = k_node128_v2 (register-resident panels + DMMA products, FP64 inside), 1 = k_node128
     cudaEvent_t fork_ev = nullptr;
@@ -535,7 +536,7 @@ struct Engine : EngineBase {
         g.A = Wb; g.B = Wb; g.C = Ab; g.M = np; g.N = np; g.K = np; g.kmode = K_GE_M; g.lower_only = 1;
         g.alpha = T(1); g.beta = T(0);
         g.rowsumsq = nullptr;
-        g.small_ctas = np <= small_tile_np ? small_tile_ctas : 0;
+        g.small_ctas = (np <= small_tile_np && small_tile_kinv) ? small_tile_ctas : 0;
         CUDA_TRY((launch_gemm_auto<T, false, false>(g, cnt, st, aligned128(), 4))); launches++;
         return HBEGP_OK;
     }
@@ -1835,6 +1836,7 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
     if (const char* s = getenv("HBEGP_NODE128")) e->use_node128 = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_NODE_V")) e->node_v = atoi(s);
     if (const char* s = getenv("HBEGP_SMALL_TILE_CTAS")) e->small_tile_ctas = atol(s);
+    if (const char* s = getenv("HBEGP_SMALL_TILE_KINV")) e->small_tile_kinv = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_SMALL_TILE_NP")) e->small_tile_np = atoi(s);
     if (const char* s = getenv("HBEGP_GROUP_MIN")) e->group_min = std::max(0, atoi(s));
     if (const char* s = getenv("HBEGP_SIDE_CNT")) e->side_max_cnt = atoi(s);
