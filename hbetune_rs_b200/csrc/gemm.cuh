@@ -439,11 +439,15 @@ constexpr int wm128() { return 64; }
 template <typename T, bool AK, bool BK_>
 inline cudaError_t launch_gemm(const GemmArgs<T>& a, int batch, cudaStream_t stream) {
     if (pick_gemm_tile<T>(a.M, a.N) == 128) return launch_gemm_cfg<T, 128, 128, wm128<T>(), 32, AK, BK_>(a, batch, stream);
-    if constexpr (std::is_same<T, double>::value) {
+    {
         const long tm = a.M / 64, tn = a.N / 64;
         const long tiles = a.lower_only ? tm * (tm + 1) / 2 : tm * tn;
-        if (a.rowsumsq == nullptr && a.raster_group == 0 && tiles * batch <= a.small_ctas)
-            return launch_gemm_cfg<T, 32, 32, 16, 16, AK, BK_>(a, batch, stream);
+        if (a.rowsumsq == nullptr && a.raster_group == 0 && tiles * batch <= a.small_ctas) {
+            // f64: 4 warps of 16x16 (2 x 2 DMMA tiles); f32: 2 warps of 32x16 (4 x 4 outputs per thread, the smallest
+            // warp tile of the FFMA micro-kernel)
+            if constexpr (std::is_same<T, double>::value) return launch_gemm_cfg<T, 32, 32, 16, 16, AK, BK_>(a, batch, stream);
+            else return launch_gemm_cfg<T, 32, 32, 32, 16, AK, BK_>(a, batch, stream);
+        }
     }
     return launch_gemm_cfg<T, 64, 64, 32, 32, AK, BK_>(a, batch, stream);
 }

@@ -1465,6 +1465,10 @@ static int configure_gemms() {
         HBEGP_CFG(32, 32, 16, 16, true, true);
         HBEGP_CFG(32, 32, 16, 16, true, false);
         HBEGP_CFG(32, 32, 16, 16, false, false);
+    } else {
+        HBEGP_CFG(32, 32, 32, 16, true, true);
+        HBEGP_CFG(32, 32, 32, 16, true, false);
+        HBEGP_CFG(32, 32, 32, 16, false, false);
     }
 #undef HBEGP_CFG
     if (std::is_same<T, float>::value) {

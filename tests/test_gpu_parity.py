@@ -102,6 +102,38 @@ def test_not_positive_definite_is_a_status_not_an_error():
     assert np.isfinite(lml[0]) and lml[0] == lml[2]
 
 
+@pytest.mark.parametrize("A", [np.float64, np.float32])
+@pytest.mark.parametrize("dup", [(0, 1), (5, 40), (3, 70), (64, 127), (10, 130), (200, 255), (100, 299)])
+def test_singular_matrices_do_not_leak_into_their_neighbours(A, dup):
+    """Duplicate training rows with zero noise make K singular at pivot max(dup): in the first or second half of a
+    bottom node, in a later node, or in the trailing part of a merge.  Rounding decides whether that pivot comes out
+    <= 0 (status 1, lml.rs:47-50: then lml = -inf and a zero gradient, fit.rs:103-113) or tiny positive, except for
+    dup = (0, 1) where it is exactly 0.  Either way the neighbours in the batch are untouched (the second-generation
+    bottom node lets non-finite values run on instead of repairing the pivot) and the context evaluates cleanly after."""
+    n, d = 300, 3
+    x, y = synth(n, d, A=A)
+    x[dup[1]] = x[dup[0]]
+    theta_bad = np.array([-800.0, 0.0, 0.0, 0.0, 0.0])
+    theta_ok = np.array([math.log(0.1), 0.0, 0.0, 0.0, 0.0])
+    with _ctx(A) as ctx:
+        ctx.set_data(x, y)
+        lml, grad, status = ctx.lml_grad_batch(np.stack([theta_ok, theta_bad, theta_ok, theta_bad, theta_ok]))
+        lml2, grad2, status2 = ctx.lml_grad_batch(theta_ok[None])
+    assert [status[0], status[2], status[4]] == [0, 0, 0] and list(status2) == [0]
+    assert status[1] == status[3]
+    if dup == (0, 1):
+        assert status[1] == 1
+    for b in (1, 3):
+        if status[b] == 1:
+            assert lml[b] == -math.inf and (grad[b] == 0).all()
+    assert np.isfinite(lml[0]) and lml[0] == lml[2] == lml[4] == lml2[0]
+    np.testing.assert_array_equal(grad[0], grad[2])
+    np.testing.assert_array_equal(grad[0], grad2[0])
+    ref = oracle_lml(theta_ok, x, y, A=A)
+    tol = 1e-9 if A == np.float64 else 1e-4
+    assert abs(lml[0] - ref.lml) <= tol * abs(ref.lml)
+
+
 def test_theta_clamping_matches_with_clamped_theta():
     A = np.float64
     x, y = synth(40, 2)
