@@ -150,6 +150,7 @@ struct EngineBase {
     bool use_node128 = true;
     long small_tile_ctas = 296;  // 32x32 GEMM tiles for grids of at most this many 64x64 CTAs ...
     int small_tile_np = 1024;    // ... at n up to this (HBEGP_SMALL_TILE_CTAS, HBEGP_SMALL_TILE_NP; gemm.cuh launch_gemm)
+    bool alpha_side = true;       // alpha on the side stream beside the K^-1 product (HBEGP_ALPHA_SIDE)
     bool small_tile_kinv = true;  // also for K^-1 = W^T W (HBEGP_SMALL_TILE_KINV)
     int group_min = 0;  // n <= 2048: fewest matrices per stream group (HBEGP_GROUP_MIN; 0 = by size)
     int node_v = 2;  // bottom node: 2 = k_node128_v2 (register-resident panels + DMMA products, FP64 inside), 1 = k_node128
@@ -567,16 +568,26 @@ struct Engine : EngineBase {
         int rc;
         if ((rc = chol_inv(st, s0, cnt, 0, np, sd))) return rc;
         if (phase < 2) return HBEGP_OK;
-        // alpha = W^T (W y)   (lml.rs:54 solves K alpha = y through the factorisation)
-        k_trmv_lower<T><<<dim3(np / 8, 1, cnt), 256, 0, st>>>(Wb, mstride(), np, (const T*)dY.p, 0, ub, np);
+        // alpha = W^T (W y)   (lml.rs:54 solves K alpha = y through the factorisation).  alpha and K^-1 = W^T W both
+        // need W only: with a side stream the three latency-bound alpha kernels run beside the K^-1 product.
+        const bool split = alpha_side && sd.st && (want_grad || want_kinv);
+        cudaStream_t sa = st;
+        if (split) {
+            CUDA_TRY(cudaEventRecord(sd.a, st));
+            CUDA_TRY(cudaStreamWaitEvent(sd.st, sd.a, 0));
+            sa = sd.st;
+        }
+        k_trmv_lower<T><<<dim3(np / 8, 1, cnt), 256, 0, sa>>>(Wb, mstride(), np, (const T*)dY.p, 0, ub, np);
         launches++;
-        k_trmv_lower_t_part<T><<<dim3(np / TILE, nchunks(), cnt), 256, 0, st>>>(Wb, mstride(), np, ub, np, tp, nchunks());
+        k_trmv_lower_t_part<T><<<dim3(np / TILE, nchunks(), cnt), 256, 0, sa>>>(Wb, mstride(), np, ub, np, tp, nchunks());
         launches++;
-        CUDA_TRY(launch_prio(k_sum_chunks<T>, dim3((np + 255) / 256, 1, cnt), dim3(256), 0, st, tp, nchunks(), np, al, (long)np));
+        CUDA_TRY(launch_prio(k_sum_chunks<T>, dim3((np + 255) / 256, 1, cnt), dim3(256), 0, sa, tp, nchunks(), np, al, (long)np));
         launches++;
+        if (split) CUDA_TRY(cudaEventRecord(sd.b, sd.st));
         if (want_grad || want_kinv) {
             if ((rc = lauum(st, Ab, Wb, cnt))) return rc;
         }
+        if (split) CUDA_TRY(cudaStreamWaitEvent(st, sd.b, 0));
         if (phase < 3) return HBEGP_OK;
         if (want_grad) {
             const size_t gsm = xsm + 2 * TILE * sizeof(T) + 8 * (size_t)(feat_chunk(d) + 2) * sizeof(double);
@@ -1840,6 +1851,7 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
     if (const char* s = getenv("HBEGP_NODE128")) e->use_node128 = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_NODE_V")) e->node_v = atoi(s);
     if (const char* s = getenv("HBEGP_SMALL_TILE_CTAS")) e->small_tile_ctas = atol(s);
+    if (const char* s = getenv("HBEGP_ALPHA_SIDE")) e->alpha_side = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_SMALL_TILE_KINV")) e->small_tile_kinv = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_SMALL_TILE_NP")) e->small_tile_np = atoi(s);
     if (const char* s = getenv("HBEGP_GROUP_MIN")) e->group_min = std::max(0, atoi(s));
