@@ -323,6 +323,31 @@ struct Engine : EngineBase {
         for (auto& kv : graphs)
             if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         graphs.clear();
+        exact_sizes.clear();
+        pad_last_cnt = -1;
+        pad_repeat = 0;
+    }
+
+    // Batch size a chunk of `cnt` evaluations runs with.  Every distinct size is a graph capture + instantiation
+    // (~20 ms at n = 1024), and a fit walks through many sizes as its runs finish, so sizes are rounded up to a
+    // multiple of 4 (copies of the last theta, results ignored: 33 distinct graphs -> 9, first fit 0.90 -> 0.27 s).
+    // The padding is not free any more now that small batches keep the GPU busy (B = 33 -> 36: +5 % per call), so a
+    // size that keeps coming back — a caller's steady loop, the first rounds of a fit — gets its exact graph after
+    // four consecutive requests (probes/pad_ab.py, profiles/r02_pad_ab.log).
+    std::vector<int> exact_sizes;
+    int pad_last_cnt = -1, pad_repeat = 0;
+    int padded_batch(int cnt) {
+        if (!(use_graphs && pad_batches && np <= 2048 && cnt > 4)) return cnt;
+        const int padded = std::min(cap, (cnt + 3) / 4 * 4);
+        if (padded == cnt) return cnt;
+        if (std::find(exact_sizes.begin(), exact_sizes.end(), cnt) != exact_sizes.end()) return cnt;
+        if (cnt == pad_last_cnt) pad_repeat++;
+        else { pad_last_cnt = cnt; pad_repeat = 1; }
+        if (pad_repeat >= 4) {
+            exact_sizes.push_back(cnt);
+            return cnt;
+        }
+        return padded;
     }
 
     ~Engine() override {
@@ -718,11 +743,8 @@ struct Engine : EngineBase {
             // Where evaluations are replayed as CUDA graphs (small n, latency bound) a few extra matrices in grid.z
             // cost next to nothing, while every distinct batch size costs a capture + instantiation: round the
             // batch up to a multiple of 4 with copies of the last theta (their results are ignored).
-            int run = cnt;
-            if (use_graphs && pad_batches && np <= 2048 && cnt > 4) {
-                run = std::min(cap, (cnt + 3) / 4 * 4);
-                for (int b = cnt; b < run; b++) std::memcpy(h_prm + (size_t)b * p(), h_prm + (size_t)(cnt - 1) * p(), sizeof(T) * p());
-            }
+            const int run = padded_batch(cnt);
+            for (int b = cnt; b < run; b++) std::memcpy(h_prm + (size_t)b * p(), h_prm + (size_t)(cnt - 1) * p(), sizeof(T) * p());
             if ((rc = run_chunk(nu2, run, grad != nullptr, false))) return rc;
             for (int b = 0; b < cnt; b++) {
                 bool bad = h_status[b] != 0 || !std::isfinite(h_out[b]);
