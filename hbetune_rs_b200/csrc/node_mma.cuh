@@ -1,4 +1,5 @@
-// The 128-wide bottom node of the factor + inverse recursion for FP64, second generation (round 2).
+// The 128-wide bottom node of the factor + inverse recursion, second generation (round 2).  FP64 arithmetic; the matrices
+// in global memory are double or (--use-32) float.
 //
 // k_node128 (kernels.cuh) spends its 59 us on (i) two 64-pivot chains with a CTA barrier and a shared-memory round
 // trip per pivot, (ii) 15 more barrier steps for the diagonal-block inverses and (iii) four 64^3 products whose operand
@@ -7,7 +8,8 @@
 // status = 1 on a non-positive pivot) and removes all three:
 //  * Cholesky in panels of 8 whose pivot chain lives in registers: every row thread holds the panel's 8x8 diagonal
 //    block (broadcast loads) and eliminates it redundantly — identical bits in every thread, no communication — while
-//    carrying its own row through the same eliminations.  Two CTA barriers per panel instead of one per pivot.
+//    carrying its own row through the same eliminations.  One CTA barrier per panel (plus two among the two panel warps)
+//    instead of one per pivot.
 //  * every product — the rank-8 trailing updates, the recursive-doubling levels of the triangular inverse, and the
 //    four 64^3 products between the halves — runs on the DMMA pipe (mma.sync.m8n8k4.f64) straight from shared
 //    memory, with the k ranges cut to the triangular structure at 8x8-tile granularity.  One warp-wide LDS feeds 256
@@ -15,10 +17,12 @@
 //  * the block being factored is held TRANSPOSED (at[k][i] = A[i][k], i >= k): a row thread's panel entries are then
 //    consecutive words across the warp, and both DMMA operands of the trailing update come from the same panel rows.
 //    Tiles have a row stride of 68 doubles (= 4 mod 16): both fragment shapes load without bank conflicts.
-//  * scaling the finished panel to the true factor (L_ik = u_ik / L_kk), the square roots and the logarithm's
-//    argument are produced by the six warps that idle during the next panel's pivot chain.
+//  * look-ahead: after a panel the two panel warps update only the rows the next panel reads and go on to its pivot
+//    chain; the other six warps apply the rest of the rank-8 update underneath it, scale the panel before to the true
+//    factor (L_ik = u_ik / L_kk), take the square roots and accumulate the logarithm's argument.
 // Measured on B200 (probes/leaf2_bench.cu, probes/lat_probe.cu): DFMA 8 cycles dependent / 2 per warp issue,
-// MUFU.RCP64H 17, DMMA 26 dependent / 16 per sub-partition, CTA barrier 15-30, shared-memory round trip 42.
+// MUFU.RCP64H 17, DMMA 26 dependent / ~17.5 per sub-partition in a saturated GEMM, ~24 per warp in short bursts
+// (probes/dmma_warm_probe.cu), CTA barrier 15-30, shared-memory round trip 42.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -449,5 +453,7 @@ __global__ void __launch_bounds__(256) k_node128_v2(TIO* __restrict__ A, TIO* __
     if (tid == 0 && fail) status[b] = 1;
     HBEGP_STAMP();
 }
+
+#undef HBEGP_STAMP
 
 }  // namespace hbegp
