@@ -377,7 +377,9 @@ def main():
                 out.update({"factor_inverse_ms": t1 - t0, "cholesky_tflops": tf, "frac": tf / pk,
                             "what": "2 n^3 / 3 FLOP per matrix (Cholesky factor + its triangular inverse), CUDA events inside the library"})
                 return out
-            for _ in range(3):
+            # warm-up: the graph of the padded batch is captured on the first call and the exact-size graph on the fourth
+            # consecutive call with the same batch size (Engine::padded_batch); both are one-off costs
+            for _ in range(8):
                 sctx.lml_grad_batch(sth, lo=slo, hi=shi)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
