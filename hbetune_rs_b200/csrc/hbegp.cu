@@ -150,6 +150,7 @@ struct EngineBase {
     bool use_node128 = true;
     long small_tile_ctas = 296;  // 32x32 GEMM tiles for grids of at most this many 64x64 CTAs ...
     int small_tile_np = 1024;    // ... at n up to this (HBEGP_SMALL_TILE_CTAS, HBEGP_SMALL_TILE_NP; gemm.cuh launch_gemm)
+    bool use_graph_update = true;  // HBEGP_GRAPH_UPDATE
     bool alpha_side = true;       // alpha on the side stream beside the K^-1 product (HBEGP_ALPHA_SIDE)
     bool small_tile_kinv = true;  // also for K^-1 = W^T W (HBEGP_SMALL_TILE_KINV)
     int group_min = 0;  // n <= 2048: fewest matrices per stream group (HBEGP_GROUP_MIN; 0 = by size)
@@ -309,7 +310,14 @@ struct Engine : EngineBase {
     struct CachedGraph {
         cudaGraphExec_t exec = nullptr;
         long long kernels = 0;
+        unsigned epoch = 0;  // graph_epoch it was captured (or last updated) in
     };
+    // New training data with the same padded size and feature count leaves the topology of every cached graph intact:
+    // only kernel arguments (n, possibly the data pointers) change.  set_data then bumps the epoch instead of dropping
+    // the graphs, and a stale graph is re-captured and patched in place with cudaGraphExecUpdate (~1 ms for the 132
+    // nodes of a 3-matrix graph at n = 500) instead of being instantiated anew — the reference's loop adds ten rows per
+    // generation (src/core/minimize.rs:331-407), so the padded size changes only every sixth generation.
+    unsigned graph_epoch = 0;
     std::map<std::tuple<int, int, int, int, int>, CachedGraph> graphs;
     bool use_graphs = true;
     bool pad_batches = true;
@@ -385,15 +393,20 @@ struct Engine : EngineBase {
         CUDA_TRY(cudaSetDevice(device));
         const void *oldx = dX.p, *oldy = dY.p;
         const bool same_shape = (n == n_ && d == d_);
+        const bool same_padded = (np == round_up(n_, TILE) && d == d_ && n > 0);
         n = n_;
         d = d_;
         np = round_up(n, TILE);
         int rc;
-        if ((rc = dX.ensure((size_t)n * d * sizeof(T)))) return rc;
+        if ((rc = dX.ensure((size_t)np * d * sizeof(T)))) return rc;  // sized by the padded row count: stable while np is
         if ((rc = dY.ensure((size_t)np * sizeof(T)))) return rc;
         if (!same_shape || oldx != dX.p || oldy != dY.p) {
-            drop_graphs();
-            cap = 0;  // workspaces are re-sized lazily
+            if (same_padded && use_graph_update) {
+                graph_epoch++;  // same topology: the cached graphs are patched on their next use (run_chunk)
+            } else {
+                drop_graphs();
+                cap = 0;  // workspaces are re-sized lazily
+            }
         }
         cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
         CUDA_TRY(cudaMemsetAsync(dY.p, 0, (size_t)np * sizeof(T), stream));
@@ -698,7 +711,7 @@ struct Engine : EngineBase {
         }
         auto key = std::make_tuple(nu2, cnt, (int)want_grad, (int)want_kinv, phase);
         auto it = graphs.find(key);
-        if (it == graphs.end()) {
+        if (it == graphs.end() || it->second.epoch != graph_epoch) {
             const long long before = launches;
             const double t_cap = now_ms();
             CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
@@ -712,15 +725,37 @@ struct Engine : EngineBase {
                 return rc;
             }
             if (ce != cudaSuccess) return fail(HBEGP_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
-            CachedGraph cg;
-            // per-node priorities (launch.h) only count in a graph instantiated with this flag
-            ce = cudaGraphInstantiate(&cg.exec, graph, LaunchPriority::get().small_ctas > 0 ? cudaGraphInstantiateFlagUseNodePriority : 0);
+            bool updated = false;
+            if (it != graphs.end()) {  // stale: same topology, new arguments
+                cudaGraphExecUpdateResultInfo info;
+                if (cudaGraphExecUpdate(it->second.exec, graph, &info) == cudaSuccess) {
+                    updated = true;
+                    it->second.epoch = graph_epoch;
+                    it->second.kernels = kernels;
+                } else {
+                    cudaGetLastError();
+                    cudaGraphExecDestroy(it->second.exec);
+                    graphs.erase(it);
+                    it = graphs.end();
+                }
+            }
+            if (!updated) {
+                CachedGraph cg;
+                // per-node priorities (launch.h) only count in a graph instantiated with this flag
+                ce = cudaGraphInstantiate(&cg.exec, graph, LaunchPriority::get().small_ctas > 0 ? cudaGraphInstantiateFlagUseNodePriority : 0);
+                if (ce != cudaSuccess) {
+                    cudaGraphDestroy(graph);
+                    return fail(HBEGP_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+                }
+                cg.kernels = kernels;
+                cg.epoch = graph_epoch;
+                if (graphs.size() > 256) drop_graphs();
+                it = graphs.emplace(key, cg).first;
+            }
             cudaGraphDestroy(graph);
-            if (ce != cudaSuccess) return fail(HBEGP_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
-            cg.kernels = kernels;
-            if (g_trace_model) fprintf(stderr, "[hbegp] graph for %d matrices: %lld kernels, capture + instantiate %.3f ms\n", cnt, kernels, now_ms() - t_cap);
-            if (graphs.size() > 256) drop_graphs();
-            it = graphs.emplace(key, cg).first;
+            if (g_trace_model)
+                fprintf(stderr, "[hbegp] graph for %d matrices: %lld kernels, capture + %s %.3f ms\n", cnt, kernels,
+                        updated ? "update" : "instantiate", now_ms() - t_cap);
         }
         CUDA_TRY(cudaGraphLaunch(it->second.exec, stream));
         launches += it->second.kernels;
@@ -1873,6 +1908,7 @@ int hbegp_ctx_create(int device, int dtype, void* stream, hbegp_ctx** out) {
     if (const char* s = getenv("HBEGP_NODE128")) e->use_node128 = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_NODE_V")) e->node_v = atoi(s);
     if (const char* s = getenv("HBEGP_SMALL_TILE_CTAS")) e->small_tile_ctas = atol(s);
+    if (const char* s = getenv("HBEGP_GRAPH_UPDATE")) e->use_graph_update = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_ALPHA_SIDE")) e->alpha_side = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_SMALL_TILE_KINV")) e->small_tile_kinv = atoi(s) != 0;
     if (const char* s = getenv("HBEGP_SMALL_TILE_NP")) e->small_tile_np = atoi(s);

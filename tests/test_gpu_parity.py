@@ -134,6 +134,31 @@ def test_singular_matrices_do_not_leak_into_their_neighbours(A, dup):
     assert abs(lml[0] - ref.lml) <= tol * abs(ref.lml)
 
 
+@pytest.mark.parametrize("A", [np.float64, np.float32])
+def test_cached_graphs_follow_new_data_of_the_same_padded_size(A):
+    """The reference's loop refits with ten more rows every generation (src/core/minimize.rs:331-407).  While the padded
+    size stays the same the context keeps its CUDA graphs and patches their arguments (cudaGraphExecUpdate) instead of
+    capturing new ones: every evaluation must equal, bit for bit, what a fresh context computes for the same data —
+    growing within one padded size, crossing into the next, shrinking back, and with the batch sizes of a fit."""
+    d = 3
+    xs, ys = synth(260, d, A=A)
+    thetas = random_thetas(5, d, seed=11)
+    with _ctx(A) as ctx:
+        for n in (130, 140, 150, 192, 193, 200, 150, 130):
+            ctx.set_data(xs[:n], ys[:n])
+            got = [ctx.lml_grad_batch(thetas[:b]) for b in (5, 3, 1, 5)]
+            with _ctx(A) as fresh:
+                fresh.set_data(xs[:n], ys[:n])
+                want = [fresh.lml_grad_batch(thetas[:b]) for b in (5, 3, 1, 5)]
+            for (l1, g1, s1), (l2, g2, s2) in zip(got, want):
+                np.testing.assert_array_equal(l1, l2)
+                np.testing.assert_array_equal(g1, g2)
+                np.testing.assert_array_equal(s1, s2)
+    ref = oracle_lml(thetas[0], xs[:130], ys[:130], A=A)
+    tol = 1e-9 if A == np.float64 else 1e-4
+    assert abs(l1[0] - ref.lml) <= tol * abs(ref.lml)
+
+
 def test_theta_clamping_matches_with_clamped_theta():
     A = np.float64
     x, y = synth(40, 2)
