@@ -4,10 +4,12 @@ import os, sys, time, json, math
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hbetune_rs_b200 as h
-from tests.util import synth
 
 d = 8
-x, y = synth(500, d, seed=3)
+_r = np.random.default_rng(3)
+x = _r.random((500, d))
+y = np.sin(2 * np.pi * x).sum(axis=1) + 0.05 * _r.standard_normal(500)
+y = (y - y.min()) / (y - y.min()).mean() + 0.05
 lo = np.array([1e-2, 1e-2] + [1e-3] * d); hi = np.array([1e1, 1e2] + [1e3] * d)
 rng = np.random.default_rng(2)
 out = {}
