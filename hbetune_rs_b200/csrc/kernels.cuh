@@ -339,7 +339,7 @@ __device__ __forceinline__ void leaf_core_nb8(T (*as)[TILE + 1], T (*ws)[TILE + 
         for (int P = 0; P < TILE / NB; P++) {
             const int c0 = NB * P;
             __syncthreads();
-            if (tid >= c0 && tid < TILE) {
+            if (tid < TILE) {  // warps 0 and 1
                 const int i = tid;
                 T U[NB][NB], x[NB], rd[NB];
 #pragma unroll
@@ -348,6 +348,9 @@ __device__ __forceinline__ void leaf_core_nb8(T (*as)[TILE + 1], T (*ws)[TILE + 
                     for (int k = 0; k <= r; k++) U[r][k] = as[c0 + r][c0 + k];
 #pragma unroll
                 for (int k = 0; k < NB; k++) x[k] = as[i][c0 + k];
+                // the diagonal rows are overwritten below by their owners: both warps must hold their copies first
+                asm volatile("bar.sync 1, 64;" ::: "memory");
+                if (i >= c0) {
                 bool bad = false;
 #pragma unroll
                 for (int j = 0; j < NB; j++) {
@@ -377,6 +380,7 @@ __device__ __forceinline__ void leaf_core_nb8(T (*as)[TILE + 1], T (*ws)[TILE + 
                         dinv[c0 + j] = dev_sqrt<T>(rd[j]);  // 1 / L_jj = sqrt(1 / u_jj)
                     }
                     if (bad) *fail = 1;
+                }
                 }
             }
             __syncthreads();
